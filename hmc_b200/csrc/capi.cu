@@ -1,0 +1,612 @@
+// C-ABI of the hmc_b200 device path (include/hmc_b200.h): context, uploads (K0 pack / flatten),
+// wave scheduling over the trellis arena, kernel launches, result download.
+#include "../../include/hmc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "forward.cuh"
+#include "traceback.cuh"
+#include "estep.cuh"
+
+using namespace hmc;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return ctx->fail(HMC_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want)
+    {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **) &p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct ScratchPool {
+    int slots = 0, K = 0;
+    int hcap = 0, ccap = 0, scap = 0;
+    DevBuf<unsigned char> mem;
+    DevBuf<Scratch> desc;
+};
+
+struct hmc_ctx {
+    int device = 0;
+    int sms = 0;
+    int threads_opt = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+
+    // panel
+    int N = 0, L = 0, Amax = 0, bits = 0, words = 0;
+    double missing_frac = 0;
+    DevBuf<u32> d_packed, d_amask;
+    DevBuf<int> d_nall, d_order;
+    std::vector<int> h_order, h_rank;
+    std::vector<int> h_nall;
+
+    // model
+    bool have_model = false;
+    DevModel dm = {};
+    DevBuf<int> d_succ, d_start, d_heads, d_head_lut;
+    DevBuf<double> d_tp, d_freq;
+    DevBuf<unsigned char> d_last;
+    DevBuf<long long> d_al_off;
+    DevBuf<signed char> d_al;
+
+    // arena + wave state
+    size_t arena_req = 0;
+    DevBuf<u64> d_arena;
+    DevBuf<unsigned long long> d_cursor;     // [0] cursor
+    DevBuf<int> d_flags;                     // [0] exhausted, [1] queue
+    DevBuf<long long> d_counters;
+    DevBuf<LocusRec> d_loci;
+    DevBuf<int> d_wave, d_status, d_final_exp, d_locus_exp;
+    std::vector<int> h_wave;                 // last wave (for hmc_get_trellis)
+    int last_K = 0, last_estep = 0;
+    ScratchPool pool, big_pool;
+
+    // results of the last resolve
+    int r_first = 0, r_count = 0, r_K = 0;
+    DevBuf<double> d_pg, d_cov, d_prior, d_post;
+    DevBuf<int> d_exp, d_nres;
+    DevBuf<signed char> d_haps;
+
+    // E-step
+    DevBuf<double> d_counts, d_pgin;
+    DevBuf<int> d_pgexp;
+    EstepTrie trie;
+
+    int64_t counters[HMC_CNT_N] = {};
+    float kernel_ms[4] = {};
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K0: genotype bit-packing, one thread per (individual, word)
+__global__ void pack_kernel(const signed char *geno, int N, int L, int bits, int words, u32 *packed)
+{
+    const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (t >= (size_t) N * words) return;
+    const int ind = (int) (t / words), wd = (int) (t % words);
+    const int per = 32 / (2 * bits);
+    const signed char *g0 = geno + ((size_t) ind * 2) * L, *g1 = g0 + L;
+    u32 v = 0;
+    for (int q = 0; q < per; ++q) {
+        const int l = wd * per + q;
+        if (l < L) {
+            const u32 c0 = (u32) (g0[l] + 1), c1 = (u32) (g1[l] + 1);
+            v |= (c0 | (c1 << bits)) << (q * 2 * bits);
+        }
+    }
+    packed[t] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NT, int CC, int KMAX>
+static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
+{
+    auto kern = forward_kernel<NT, CC, KMAX>;
+    const size_t smem = forward_smem_bytes<CC>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, NT, smem);
+    kern<<<grid, NT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NT, int CC>
+static cudaError_t launch_forward_k(int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
+{
+    switch (kmax) {
+        case 1: return launch_forward_t<NT, CC, 1>(p, grid, st, occ);
+        case 4: return launch_forward_t<NT, CC, 4>(p, grid, st, occ);
+        case 10: return launch_forward_t<NT, CC, 10>(p, grid, st, occ);
+        case 16: return launch_forward_t<NT, CC, 16>(p, grid, st, occ);
+        default: return launch_forward_t<NT, CC, 32>(p, grid, st, occ);
+    }
+}
+
+static cudaError_t launch_forward(int nt, int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
+{
+    switch (nt) {
+        case 32: return launch_forward_k<32, 128>(kmax, p, grid, st, occ);
+        case 64: return launch_forward_k<64, 256>(kmax, p, grid, st, occ);
+        case 128: return launch_forward_k<128, 512>(kmax, p, grid, st, occ);
+        default: return launch_forward_k<256, 1024>(kmax, p, grid, st, occ);
+    }
+}
+
+static int kmax_for(int K) { return K <= 1 ? 1 : K <= 4 ? 4 : K <= 10 ? 10 : K <= 16 ? 16 : 32; }
+
+static cudaError_t launch_traceback(int kmax, const TraceParams &p, cudaStream_t st)
+{
+    const int wpb = 4;
+    const int grid = (p.n_wave + wpb - 1) / wpb;
+    switch (kmax) {
+        case 1: traceback_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 4: traceback_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 10: traceback_kernel<10><<<grid, wpb * 32, 0, st>>>(p); break;
+        case 16: traceback_kernel<16><<<grid, wpb * 32, 0, st>>>(p); break;
+        default: traceback_kernel<32><<<grid, wpb * 32, 0, st>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+
+// size / (re)build a scratch pool: one Scratch per persistent CTA
+static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap, int ccap, int hcap)
+{
+    if (pl.slots >= slots && pl.K >= K && pl.scap == scap && pl.ccap == ccap && pl.hcap == hcap) return HMC_OK;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+    const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_s = al((size_t) (scap + 1) * 4);
+    const size_t b_like = al((size_t) scap * K * 8), b_meta = al((size_t) scap * 8);
+    const size_t per = b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 2 * b_meta;
+    CK(pl.mem.ensure(per * slots));
+    CK(pl.desc.ensure(slots));
+    std::vector<Scratch> h(slots);
+    for (int i = 0; i < slots; ++i) {
+        unsigned char *b = pl.mem.p + per * i;
+        Scratch &s = h[i];
+        s.hcap = hcap; s.ccap = ccap; s.scap = scap;
+        s.keys = (u64 *) b; b += b_keys;
+        s.ord = (u32 *) b; b += b_u32;
+        s.cnt = (u32 *) b; b += b_u32;
+        s.nidx = nullptr;
+        s.cand = (int *) b; b += b_c;
+        s.arr = (int *) b; b += b_c;
+        s.aoff = (int *) b; b += b_s;
+        s.slot_of = (int *) b; b += b_s;
+        s.like[0] = (double *) b; b += b_like;
+        s.like[1] = (double *) b; b += b_like;
+        s.meta[0] = (u64 *) b; b += b_meta;
+        s.meta[1] = (u64 *) b; b += b_meta;
+    }
+    CK(cudaMemcpyAsync(pl.desc.p, h.data(), sizeof(Scratch) * slots, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    pl.slots = slots; pl.K = K; pl.scap = scap; pl.ccap = ccap; pl.hcap = hcap;
+    return HMC_OK;
+}
+
+static int ensure_arena(hmc_ctx *ctx)
+{
+    if (ctx->d_arena.p) return HMC_OK;
+    size_t want = ctx->arena_req;
+    if (want == 0) {
+        size_t fr = 0, tot = 0;
+        CK(cudaMemGetInfo(&fr, &tot));
+        want = (size_t) (fr * 0.6);
+        const char *env = getenv("HMC_B200_ARENA_MB");
+        if (env) want = (size_t) atoll(env) << 20;
+    }
+    CK(ctx->d_arena.ensure(want / 8));
+    return HMC_OK;
+}
+
+static int pick_threads(const hmc_ctx *ctx)
+{
+    const char *env = getenv("HMC_B200_THREADS");
+    int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
+    if (nt == 0) nt = ctx->missing_frac > 0.02 ? 128 : (ctx->missing_frac > 0.002 ? 64 : 32);
+    if (nt != 32 && nt != 64 && nt != 128 && nt != 256) nt = 128;
+    return nt;
+}
+
+// Runs the forward kernel (and, unless estep, the traceback) over individuals [first, first+count) in
+// arena waves.  `after_wave`, when set, is called once per wave with the trellis still live (E-step).
+template <typename AfterWave>
+static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, int estep, AfterWave after_wave)
+{
+    if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
+    if (!ctx->have_model) return ctx->fail(HMC_ERR_INVALID, "hmc_set_model has not been called");
+    if (first < 0 || count < 0 || first + count > ctx->N) return ctx->fail(HMC_ERR_INVALID, "individual range [%d,%d) outside the panel", first, first + count);
+    if (K < 1 || K > HMC_MAX_K) return ctx->fail(HMC_ERR_LIMIT, "sample size %d outside [1,%d]", K, HMC_MAX_K);
+    const int L = ctx->L;
+    int rc = ensure_arena(ctx);
+    if (rc) return rc;
+    CK(ctx->d_cursor.ensure(1));
+    CK(ctx->d_flags.ensure(2));
+    CK(ctx->d_counters.ensure(8));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(long long), ctx->stream));
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
+
+    const int nt = pick_threads(ctx);
+    const int kmax = kmax_for(K);
+    int occ = 1;
+    FwdParams fp = {};
+    CK(launch_forward(nt, kmax, fp, 0, ctx->stream, &occ));
+    if (occ < 1) occ = 1;
+    const int max_slots = ctx->sms * occ;
+
+    // wave capacity is bounded by the per-(individual, index) record table
+    const size_t max_loci_bytes = (size_t) 6 << 30;
+    int wave_cap = (int) std::min<size_t>((size_t) count, std::max<size_t>(1, max_loci_bytes / ((size_t) (L + 1) * sizeof(LocusRec))));
+    CK(ctx->d_loci.ensure((size_t) wave_cap * (L + 1)));
+    CK(ctx->d_wave.ensure(wave_cap));
+    CK(ctx->d_status.ensure(wave_cap));
+    CK(ctx->d_final_exp.ensure(wave_cap));
+    if (estep && (flags & HMC_FLAG_SCALED)) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * (L + 1)));
+
+    // pending individuals, heaviest first
+    std::vector<int> pending;
+    pending.reserve(count);
+    for (int q = 0; q < ctx->N; ++q) { const int ind = ctx->h_order[q]; if (ind >= first && ind < first + count) pending.push_back(ind); }
+    std::vector<int> big;
+    std::vector<int> h_status;
+    bool big_mode = false;
+    int waves = 0, launches = 0;
+
+    while (!pending.empty() || (!big_mode && !big.empty())) {
+        if (pending.empty()) { big_mode = true; pending.swap(big); }
+        const int n_wave = (int) std::min<size_t>(pending.size(), (size_t) wave_cap);
+        ScratchPool &pl = big_mode ? ctx->big_pool : ctx->pool;
+        int slots;
+        if (big_mode) { slots = std::min(n_wave, 4); rc = build_pool(ctx, pl, slots, K, 1 << 22, 1 << 24, 1 << 25); }
+        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, K, 1 << 15, 1 << 17, 1 << 18); }
+        if (rc) return rc;
+        ctx->h_wave.assign(pending.begin(), pending.begin() + n_wave);
+        CK(cudaMemcpyAsync(ctx->d_wave.p, ctx->h_wave.data(), sizeof(int) * n_wave, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cursor.p, 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_status.p, 0, sizeof(int) * n_wave, ctx->stream));
+
+        fp.panel.N = ctx->N; fp.panel.L = L; fp.panel.Amax = ctx->Amax; fp.panel.bits = ctx->bits; fp.panel.words = ctx->words;
+        fp.panel.packed = ctx->d_packed.p; fp.panel.nall = ctx->d_nall.p; fp.panel.amask = ctx->d_amask.p; fp.panel.order = ctx->d_order.p;
+        fp.model = ctx->dm;
+        fp.arena.base = ctx->d_arena.p; fp.arena.capacity = (long long) ctx->d_arena.n; fp.arena.cursor = ctx->d_cursor.p; fp.arena.exhausted = ctx->d_flags.p;
+        fp.scratch = pl.desc.p;
+        fp.loci = ctx->d_loci.p; fp.wave = ctx->d_wave.p; fp.n_wave = n_wave; fp.K = K; fp.estep = estep;
+        fp.scaled = (flags & HMC_FLAG_SCALED) ? 1 : 0;
+        fp.status = ctx->d_status.p; fp.final_exp = ctx->d_final_exp.p;
+        fp.locus_exp = (estep && fp.scaled) ? ctx->d_locus_exp.p : nullptr;
+        fp.queue = ctx->d_flags.p + 1; fp.counters = ctx->d_counters.p;
+
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CK(launch_forward(nt, kmax, fp, slots, ctx->stream, nullptr));
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ++launches;
+        if (!estep) {
+            TraceParams tp = {};
+            tp.panel = fp.panel; tp.model = fp.model; tp.arena = ctx->d_arena.p; tp.loci = ctx->d_loci.p; tp.wave = ctx->d_wave.p;
+            tp.status = ctx->d_status.p; tp.final_exp = ctx->d_final_exp.p; tp.n_wave = n_wave; tp.K = K; tp.first = first;
+            tp.pg = ctx->d_pg.p; tp.cov = ctx->d_cov.p; tp.prior = ctx->d_prior.p; tp.post = ctx->d_post.p; tp.exp2 = ctx->d_exp.p; tp.nres = ctx->d_nres.p;
+            tp.haps = ctx->d_haps.p;
+            CK(launch_traceback(kmax, tp, ctx->stream));
+            ++launches;
+        }
+        CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        h_status.resize(n_wave);
+        CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, sizeof(int) * n_wave, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->kernel_ms[0] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->kernel_ms[1] += ms;
+        rc = after_wave(fp, n_wave, h_status, launches);
+        if (rc) return rc;
+
+        std::vector<int> again;
+        int done = 0;
+        for (int q = 0; q < n_wave; ++q) {
+            switch (h_status[q]) {
+                case ST_DONE: ++done; break;
+                case ST_NOMEM: case ST_PENDING: again.push_back(ctx->h_wave[q]); break;
+                case ST_TOO_BIG:
+                    if (big_mode) return ctx->fail(HMC_ERR_LIMIT, "individual %d exceeds the per-locus state capacity", ctx->h_wave[q]);
+                    big.push_back(ctx->h_wave[q]);
+                    break;
+                case ST_NO_HEAD: return ctx->fail(HMC_ERR_NO_HEAD, "individual %d: Can not find matching pattern!", ctx->h_wave[q]);
+                default: return ctx->fail(HMC_ERR_CUDA, "individual %d: unexpected status %d", ctx->h_wave[q], h_status[q]);
+            }
+        }
+        ++waves;
+        if (done == 0 && big.empty() && !again.empty() && (int) again.size() == n_wave)
+            return ctx->fail(HMC_ERR_NOMEM, "trellis arena (%zu MB) cannot hold a single individual", ctx->d_arena.n * 8 >> 20);
+        pending.erase(pending.begin(), pending.begin() + n_wave);
+        pending.insert(pending.begin(), again.begin(), again.end());
+    }
+    long long hc[8];
+    CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+    ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
+    ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5];
+    ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
+    ctx->last_K = K; ctx->last_estep = estep;
+    return HMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *hmc_version(void) { return "hmc_b200 0.1 sm_100a"; }
+
+int hmc_ctx_create(hmc_ctx **out, int device, size_t arena_bytes, int threads)
+{
+    if (!out) return HMC_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return HMC_ERR_NO_DEVICE;
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) return HMC_ERR_NO_DEVICE;
+    if (pr.major != 10) return HMC_ERR_NO_DEVICE;      // the kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return HMC_ERR_NO_DEVICE;
+    hmc_ctx *ctx = new hmc_ctx;
+    ctx->device = device; ctx->sms = pr.multiProcessorCount; ctx->arena_req = arena_bytes; ctx->threads_opt = threads;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HMC_ERR_CUDA; }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    *out = ctx;
+    return HMC_OK;
+}
+
+void hmc_ctx_destroy(hmc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_packed.release(); ctx->d_amask.release(); ctx->d_nall.release(); ctx->d_order.release();
+    ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
+    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release();
+    ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
+    ctx->d_wave.release(); ctx->d_status.release(); ctx->d_final_exp.release(); ctx->d_locus_exp.release();
+    ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
+    ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
+    ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
+    ctx->trie.release();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *hmc_last_error(const hmc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, const int32_t *n_alleles, const double *allele_freq)
+{
+    if (!ctx || N <= 0 || L <= 0 || !geno || !n_alleles || !allele_freq) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_set_panel: bad argument") : HMC_ERR_INVALID;
+    if (Amax < 1 || Amax > HMC_MAX_ALLELES) return ctx->fail(HMC_ERR_LIMIT, "Amax %d outside [1,%d]", Amax, HMC_MAX_ALLELES);
+    CK(cudaSetDevice(ctx->device));
+    ctx->N = N; ctx->L = L; ctx->Amax = Amax;
+    ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
+    const int per = 32 / (2 * ctx->bits);
+    ctx->words = (L + per - 1) / per;
+    // allele mask, work order (most missing genotypes first: they carry the largest state sets)
+    std::vector<u32> amask(L, 0);
+    ctx->h_nall.assign(n_alleles, n_alleles + L);
+    for (int l = 0; l < L; ++l) {
+        if (n_alleles[l] < 0 || n_alleles[l] > Amax) return ctx->fail(HMC_ERR_INVALID, "n_alleles[%d] = %d outside [0,%d]", l, n_alleles[l], Amax);
+        for (int j = 0; j < n_alleles[l]; ++j) if (allele_freq[(size_t) l * Amax + j] > 0) amask[l] |= 1u << j;
+    }
+    std::vector<int> miss(N, 0);
+    size_t tot_miss = 0;
+    for (int i = 0; i < N; ++i) {
+        const int8_t *g0 = geno + ((size_t) i * 2) * L, *g1 = g0 + L;
+        int m = 0;
+        for (int l = 0; l < L; ++l) {
+            if (g0[l] >= Amax || g1[l] >= Amax) return ctx->fail(HMC_ERR_INVALID, "allele index out of range at individual %d locus %d", i, l);
+            m += (g0[l] < 0) + (g1[l] < 0);
+        }
+        miss[i] = m; tot_miss += m;
+    }
+    ctx->missing_frac = (double) tot_miss / ((double) N * L * 2);
+    ctx->h_order.resize(N);
+    for (int i = 0; i < N; ++i) ctx->h_order[i] = i;
+    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) { return miss[a] > miss[b]; });
+    CK(ctx->d_packed.ensure((size_t) N * ctx->words));
+    CK(ctx->d_amask.ensure(L));
+    CK(ctx->d_nall.ensure(L));
+    CK(ctx->d_order.ensure(N));
+    DevBuf<signed char> raw;
+    CK(raw.ensure((size_t) N * 2 * L));
+    CK(cudaMemcpyAsync(raw.p, geno, (size_t) N * 2 * L, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_amask.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_nall.p, n_alleles, sizeof(int) * L, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t nthr = (size_t) N * ctx->words;
+    pack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, ctx->stream>>>(raw.p, N, L, ctx->bits, ctx->words, ctx->d_packed.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    raw.release();
+    return HMC_OK;
+}
+
+int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const int32_t *end, const double *freq, const double *tp,
+                  const int32_t *succ, const int64_t *al_off, const int8_t *alleles, int n_heads, const int32_t *heads)
+{
+    if (!ctx || P <= 0 || !start || !end || !freq || !tp || !succ || !al_off || !alleles || !heads) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_set_model: bad argument") : HMC_ERR_INVALID;
+    if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_model before hmc_set_panel");
+    if (head_len < 1 || head_len > 8 || head_len > ctx->L) return ctx->fail(HMC_ERR_LIMIT, "head length %d outside [1,8]", head_len);
+    CK(cudaSetDevice(ctx->device));
+    const int A = ctx->Amax;
+    std::vector<unsigned char> last(P);
+    for (int i = 0; i < P; ++i) {
+        if (al_off[i + 1] - al_off[i] != end[i] - start[i] || end[i] <= start[i] || end[i] > ctx->L || start[i] < 0)
+            return ctx->fail(HMC_ERR_INVALID, "pattern %d: inconsistent start/end/alleles", i);
+        last[i] = (unsigned char) alleles[al_off[i + 1] - 1];
+    }
+    // head lookup: mixed-radix code over the first head_len loci, locus 0 most significant
+    int stride[8] = {0};
+    long long size = 1;
+    for (int j = head_len - 1; j >= 0; --j) { stride[j] = (int) size; size *= std::max(1, ctx->h_nall[j]); if (size > (1 << 20)) return ctx->fail(HMC_ERR_LIMIT, "head table too large"); }
+    std::vector<int> lut((size_t) size, -1);
+    for (int h = 0; h < n_heads; ++h) {
+        const int id = heads[h];
+        if (id < 0 || id >= P || start[id] != 0 || end[id] != head_len) return ctx->fail(HMC_ERR_INVALID, "head %d is not a start-0 pattern of length head_len", id);
+        long long code = 0;
+        for (int j = 0; j < head_len; ++j) code += (long long) alleles[al_off[id] + j] * stride[j];
+        lut[(size_t) code] = id;
+    }
+    CK(ctx->d_succ.ensure((size_t) P * A)); CK(ctx->d_start.ensure(P)); CK(ctx->d_tp.ensure(P)); CK(ctx->d_freq.ensure(P)); CK(ctx->d_last.ensure(P));
+    CK(ctx->d_al_off.ensure(P + 1)); CK(ctx->d_al.ensure((size_t) al_off[P] + 1)); CK(ctx->d_heads.ensure(std::max(1, n_heads))); CK(ctx->d_head_lut.ensure(lut.size()));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_succ.p, succ, sizeof(int) * (size_t) P * A, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_start.p, start, sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_tp.p, tp, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_freq.p, freq, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_last.p, last.data(), P, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_al_off.p, al_off, sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_al.p, alleles, (size_t) al_off[P], cudaMemcpyHostToDevice, st));
+    if (n_heads > 0) CK(cudaMemcpyAsync(ctx->d_heads.p, heads, sizeof(int) * n_heads, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_head_lut.p, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    DevModel &m = ctx->dm;
+    m.P = P; m.head_len = head_len; m.n_heads = n_heads; m.Amax = A;
+    m.succ = ctx->d_succ.p; m.tp = ctx->d_tp.p; m.freq = ctx->d_freq.p; m.start = ctx->d_start.p; m.last = ctx->d_last.p;
+    m.al_off = ctx->d_al_off.p; m.al = ctx->d_al.p; m.heads = ctx->d_heads.p; m.head_lut = ctx->d_head_lut.p;
+    for (int j = 0; j < 8; ++j) m.head_stride[j] = stride[j];
+    ctx->have_model = true;
+    return HMC_OK;
+}
+
+int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned flags)
+{
+    if (!ctx) return HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (count <= 0 || K < 1 || K > HMC_MAX_K) return ctx->fail(HMC_ERR_INVALID, "hmc_resolve_all: bad count/K");
+    const int L = ctx->L;
+    CK(ctx->d_pg.ensure(count)); CK(ctx->d_cov.ensure(count)); CK(ctx->d_exp.ensure(count)); CK(ctx->d_nres.ensure(count));
+    CK(ctx->d_prior.ensure((size_t) count * K)); CK(ctx->d_post.ensure((size_t) count * K));
+    CK(ctx->d_haps.ensure((size_t) count * K * 2 * L));
+    ctx->r_first = first; ctx->r_count = count; ctx->r_K = K;
+    return run_waves(ctx, first, count, K, flags, 0, [](const FwdParams &, int, const std::vector<int> &, int &) { return 0; });
+}
+
+int hmc_fetch_results(hmc_ctx *ctx, double *out_pg, int32_t *out_exp, double *out_cov, int32_t *out_nres, double *out_prior, double *out_post,
+                      int8_t *out_haps, double *out_ll)
+{
+    if (!ctx || ctx->r_count <= 0) return ctx ? ctx->fail(HMC_ERR_INVALID, "no results to fetch") : HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->r_count, K = ctx->r_K;
+    cudaStream_t st = ctx->stream;
+    std::vector<double> pg;
+    std::vector<int> ex;
+    if (out_ll && !out_pg) { pg.resize(n); out_pg = pg.data(); }
+    if (out_ll && !out_exp) { ex.resize(n); out_exp = ex.data(); }
+    if (out_pg) CK(cudaMemcpyAsync(out_pg, ctx->d_pg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (out_exp) CK(cudaMemcpyAsync(out_exp, ctx->d_exp.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (out_cov) CK(cudaMemcpyAsync(out_cov, ctx->d_cov.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (out_nres) CK(cudaMemcpyAsync(out_nres, ctx->d_nres.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (out_prior) CK(cudaMemcpyAsync(out_prior, ctx->d_prior.p, sizeof(double) * (size_t) n * K, cudaMemcpyDeviceToHost, st));
+    if (out_post) CK(cudaMemcpyAsync(out_post, ctx->d_post.p, sizeof(double) * (size_t) n * K, cudaMemcpyDeviceToHost, st));
+    if (out_haps) CK(cudaMemcpyAsync(out_haps, ctx->d_haps.p, (size_t) n * K * 2 * ctx->L, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (out_ll) {   // HaploModel.cpp:110, in individual order
+        double ll = 0;
+        for (int i = 0; i < n; ++i) ll += out_exp[i] ? (std::log(out_pg[i]) - out_exp[i] * M_LN2) : std::log(out_pg[i]);
+        *out_ll = ll;
+    }
+    return HMC_OK;
+}
+
+int hmc_resolve_all(hmc_ctx *ctx, int first, int count, int K, unsigned flags, double *out_pg, int32_t *out_exp, double *out_cov,
+                    int32_t *out_nres, double *out_prior, double *out_post, int8_t *out_haps, double *out_ll)
+{
+    int rc = hmc_resolve_all_device(ctx, first, count, K, flags);
+    if (rc) return rc;
+    return hmc_fetch_results(ctx, out_pg, out_exp, out_cov, out_nres, out_prior, out_post, out_haps, out_ll);
+}
+
+void hmc_normalise_counts(int Pc, int N, double *freq, double *prefix, double *tp)
+{
+    for (int i = 0; i < Pc; ++i) {      // HaploBuilder.cpp:317-331
+        double f = std::min(freq[i], (double) N);
+        const double pf = std::min(prefix[i], (double) N);
+        f = std::min(f, pf);
+        freq[i] = f / N;
+        prefix[i] = pf / N;
+        const double t = pf > 0 ? f / pf : f / N;
+        if (tp) tp[i] = t < 1.0 ? t : 1.0;      // HaploPattern::setTransitionProb clamp, HaploPattern.h:47
+    }
+}
+
+int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N])
+{
+    if (!ctx || !out) return HMC_ERR_INVALID;
+    memcpy(out, ctx->counters, sizeof ctx->counters);
+    return HMC_OK;
+}
+
+int hmc_get_kernel_ms(hmc_ctx *ctx, float out[4])
+{
+    if (!ctx || !out) return HMC_ERR_INVALID;
+    memcpy(out, ctx->kernel_ms, sizeof ctx->kernel_ms);
+    return HMC_OK;
+}
+
+int64_t hmc_get_trellis(hmc_ctx *ctx, int individual, int32_t *counts, int64_t capacity, int32_t *ida, int32_t *idb, double *alpha, double *beta)
+{
+    if (!ctx || !counts) return HMC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    int w = -1;
+    for (size_t q = 0; q < ctx->h_wave.size(); ++q) if (ctx->h_wave[q] == individual) { w = (int) q; break; }
+    if (w < 0) return ctx->fail(HMC_ERR_INVALID, "individual %d is not in the last wave", individual);
+    const int L = ctx->L;
+    std::vector<LocusRec> rec(L + 1);
+    if (cudaMemcpy(rec.data(), ctx->d_loci.p + (size_t) w * (L + 1), sizeof(LocusRec) * (L + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return ctx->fail(HMC_ERR_CUDA, "trellis record copy failed");
+    int64_t tot = 0;
+    for (int l = 0; l <= L; ++l) {
+        const int S = (l < ctx->dm.head_len) ? 0 : rec[l].count;
+        counts[l] = S;
+        if (S <= 0) continue;
+        if (tot + S > capacity) return ctx->fail(HMC_ERR_INVALID, "trellis capacity too small");
+        const BlockLayout b = block_layout(S, ctx->last_K, ctx->last_estep);
+        const u64 *blk = ctx->d_arena.p + rec[l].off;
+        cudaError_t e = cudaSuccess;
+        if (ida) e = cudaMemcpy(ida + tot, blk + b.ida, sizeof(int) * S, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && idb) e = cudaMemcpy(idb + tot, blk + b.idb, sizeof(int) * S, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && alpha) e = cudaMemcpy(alpha + tot, blk + b.alpha, sizeof(double) * S, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && beta && ctx->last_estep) e = cudaMemcpy(beta + tot, blk + b.beta, sizeof(double) * S, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return ctx->fail(HMC_ERR_CUDA, "trellis copy failed: %s", cudaGetErrorString(e));
+        tot += S;
+    }
+    return tot;
+}
+
+}  // extern "C"
+
+#include "estep_capi.inl"

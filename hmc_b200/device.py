@@ -1,0 +1,168 @@
+"""ctypes binding of the C-ABI (include/hmc_b200.h) -- the device path of HaploBuilder.
+
+There is no CPU fallback: if libhmc_b200.so is missing or no B200 is present, constructing a
+``DeviceBuilder`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhmc_b200.so")
+_LIB = None
+
+FLAG_SCALED = 1
+FLAG_KEEP_TRELLIS = 2
+CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps", "launches", "_")
+
+EXPORTS = [
+    "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",
+    "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
+    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis",
+]
+
+
+class HmcError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise HmcError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        L = C.CDLL(_SO)
+        L.hmc_version.restype = C.c_char_p
+        L.hmc_last_error.restype = C.c_char_p
+        L.hmc_last_error.argtypes = [C.c_void_p]
+        L.hmc_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_int]
+        L.hmc_ctx_destroy.argtypes = [C.c_void_p]
+        L.hmc_set_panel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmc_set_model.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+        L.hmc_resolve_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 8
+        L.hmc_resolve_all_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint]
+        L.hmc_fetch_results.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.hmc_estimate_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int] + [C.c_void_p] * 7
+        L.hmc_estimate_counts_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p)]
+        L.hmc_normalise_counts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmc_normalise_counts.restype = None
+        L.hmc_get_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.hmc_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.hmc_get_trellis.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+        L.hmc_get_trellis.restype = C.c_longlong
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceBuilder:
+    """The HaploBuilder surface (HaploBuilder.h:33-54) batched over individuals, on one B200."""
+
+    def __init__(self, device: int = 0, arena_bytes: int = 0, threads: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().hmc_ctx_create(C.byref(self._h), device, arena_bytes, threads)
+        if rc != 0:
+            self._h = None
+            raise HmcError(f"hmc_ctx_create failed with status {rc} (no B200 / sm_100a device?) -- there is no CPU fallback")
+        self.N = self.L = self.Amax = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hmc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise HmcError(f"status {rc}: {lib().hmc_last_error(self._h).decode()}")
+        return rc
+
+    def set_panel(self, geno: np.ndarray, n_alleles: np.ndarray, allele_freq: np.ndarray):
+        g = np.ascontiguousarray(geno, np.int8)
+        self.N, _, self.L = g.shape
+        na = np.ascontiguousarray(n_alleles, np.int32)
+        af = np.ascontiguousarray(allele_freq, np.float64)
+        self.Amax = af.shape[1]
+        self._ck(lib().hmc_set_panel(self._h, self.N, self.L, self.Amax, _p(g), _p(na), _p(af)))
+
+    def set_model(self, m: dict):
+        """m: start,end,freq,tp,succ[P][Amax],al_off,al,heads,head_len (the layout of Oracle.export_model / HaploModel.export_model)."""
+        a = {k: np.ascontiguousarray(m[k], dt) for k, dt in (("start", np.int32), ("end", np.int32), ("freq", np.float64), ("tp", np.float64),
+                                                               ("succ", np.int32), ("al_off", np.int64), ("al", np.int8), ("heads", np.int32))}
+        self._ck(lib().hmc_set_model(self._h, int(m["P"]), int(m["head_len"]), _p(a["start"]), _p(a["end"]), _p(a["freq"]), _p(a["tp"]),
+                                     _p(a["succ"]), _p(a["al_off"]), _p(a["al"]), len(a["heads"]), _p(a["heads"])))
+
+    def _alloc(self, count, K, haps):
+        r = dict(pg=np.zeros(count), exp=np.zeros(count, np.int32), coverage=np.zeros(count), nres=np.zeros(count, np.int32),
+                 prior=np.zeros((count, K)), posterior=np.zeros((count, K)), ll=np.zeros(1))
+        r["haps"] = np.zeros((count, K, 2, self.L), np.int8) if haps else None
+        return r
+
+    def resolve_all(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0, haps: bool = True) -> dict:
+        count = self.N - first if count is None else count
+        r = self._alloc(count, K, haps)
+        self._ck(lib().hmc_resolve_all(self._h, first, count, K, flags, _p(r["pg"]), _p(r["exp"]), _p(r["coverage"]), _p(r["nres"]),
+                                       _p(r["prior"]), _p(r["posterior"]), _p(r["haps"]), _p(r["ll"])))
+        r["ll"] = float(r["ll"][0])
+        return r
+
+    def resolve_all_device(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0):
+        count = self.N - first if count is None else count
+        self._ck(lib().hmc_resolve_all_device(self._h, first, count, K, flags))
+        self._last = (count, K)
+
+    def fetch_results(self, haps: bool = True) -> dict:
+        count, K = self._last
+        r = self._alloc(count, K, haps)
+        self._ck(lib().hmc_fetch_results(self._h, _p(r["pg"]), _p(r["exp"]), _p(r["coverage"]), _p(r["nres"]), _p(r["prior"]),
+                                         _p(r["posterior"]), _p(r["haps"]), _p(r["ll"])))
+        r["ll"] = float(r["ll"][0])
+        return r
+
+    def estimate_counts(self, start, al_off, al, pg, pg_exp=None, first: int = 0, count: int | None = None, flags: int = 0):
+        count = self.N - first if count is None else count
+        start = np.ascontiguousarray(start, np.int32); al_off = np.ascontiguousarray(al_off, np.int64); al = np.ascontiguousarray(al, np.int8)
+        pg = np.ascontiguousarray(pg, np.float64)
+        pe = None if pg_exp is None else np.ascontiguousarray(pg_exp, np.int32)
+        Pc = len(start)
+        f, pf = np.zeros(Pc), np.zeros(Pc)
+        self._ck(lib().hmc_estimate_counts(self._h, first, count, flags, Pc, _p(start), _p(al_off), _p(al), _p(pg), _p(pe), _p(f), _p(pf)))
+        return f, pf
+
+    @staticmethod
+    def normalise_counts(freq, prefix, N):
+        f = np.array(freq, np.float64); pf = np.array(prefix, np.float64); tp = np.zeros_like(f)
+        lib().hmc_normalise_counts(len(f), N, _p(f), _p(pf), _p(tp))
+        return f, pf, tp
+
+    def counters(self) -> dict:
+        out = np.zeros(8, np.int64)
+        self._ck(lib().hmc_get_counters(self._h, _p(out)))
+        return {k: int(v) for k, v in zip(CNT_NAMES, out) if k != "_"}
+
+    def kernel_ms(self) -> dict:
+        out = np.zeros(4, np.float32)
+        self._ck(lib().hmc_get_kernel_ms(self._h, _p(out)))
+        return dict(forward=float(out[0]), traceback=float(out[1]), backward=float(out[2]), estep=float(out[3]))
+
+    def trellis(self, individual: int, capacity: int = 1 << 22, beta: bool = False) -> dict:
+        counts = np.zeros(self.L + 1, np.int32)
+        ida = np.zeros(capacity, np.int32); idb = np.zeros(capacity, np.int32); alpha = np.zeros(capacity)
+        bt = np.zeros(capacity) if beta else None
+        tot = self._ck(lib().hmc_get_trellis(self._h, individual, _p(counts), capacity, _p(ida), _p(idb), _p(alpha), _p(bt)))
+        return dict(counts=counts, ida=ida[:tot], idb=idb[:tot], alpha=alpha[:tot], beta=None if bt is None else bt[:tot])

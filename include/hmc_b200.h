@@ -1,0 +1,136 @@
+/*
+ * hmc_b200 -- C-ABI of the B200 (sm_100a) HaploBuilder / EM E-step path of HMC.
+ *
+ * This is the drop-in boundary for the reference's HaploBuilder (HaploBuilder.h:33-54) as driven by
+ * HaploModel::resolveAll (HaploModel.cpp:79-115) and PatternManager::estimateFrequency /
+ * estimatePatterns (PatternManager.cpp:347-410).  The reference has no FFI of its own (it is one
+ * single-threaded C++ program); the calls are batched over individuals because a per-individual
+ * call (the reference's `resolve`) would serialise the GPU.  INTEGRATION.md shows the reference-side
+ * glue a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is caller-owned HOST memory unless the name says
+ *     otherwise; the context owns all device memory;
+ *   - every function returns HMC_OK (0) or a negative hmc_status; nothing calls exit() (the
+ *     reference does: Logger::error + exit(1), e.g. HaploBuilder.cpp:215-218);
+ *   - alleles are per-locus allele INDICES in GenoData::getAlleleIndex order (GenoData.cpp:27-44,
+ *     symbols sorted ascending, GenoData.cpp:96-98); -1 is the missing allele (Allele.h:13);
+ *   - pattern ids are positions in the arrays handed to hmc_set_model, exactly the ids
+ *     PatternManager::initialize assigns (PatternManager.cpp:300-302);
+ *   - all probabilities are IEEE fp64; products and sums are evaluated in the reference's order
+ *     without FMA contraction, so alpha, P(G) and priors are bit-identical to the reference;
+ *   - one host thread per context (the reference is non-reentrant too).
+ *
+ * There is no CPU fallback: without a CUDA device hmc_ctx_create fails with HMC_ERR_NO_DEVICE.
+ */
+#ifndef HMC_B200_H
+#define HMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hmc_ctx hmc_ctx;
+
+typedef enum hmc_status {
+    HMC_OK = 0,
+    HMC_ERR_NO_DEVICE = -1,     /* no CUDA device / wrong architecture */
+    HMC_ERR_CUDA = -2,          /* a CUDA call failed; see hmc_last_error */
+    HMC_ERR_INVALID = -3,       /* bad argument or call order */
+    HMC_ERR_LIMIT = -4,         /* a documented capacity was exceeded (alleles per locus, K, states per locus) */
+    HMC_ERR_NOMEM = -5,         /* the trellis arena cannot hold even one individual */
+    HMC_ERR_NO_HEAD = -6        /* "Can not find matching pattern!" (HaploBuilder.cpp:215-218) */
+} hmc_status;
+
+/* flags for hmc_resolve_all / hmc_estimate_counts */
+#define HMC_FLAG_SCALED        1u   /* exponent-only rescaling by 2^512 when max alpha < 2^-512; off = the
+                                       reference's raw fp64 products, bit for bit */
+#define HMC_FLAG_KEEP_TRELLIS  2u   /* keep the last wave's trellis on the device for hmc_get_trellis (tests) */
+
+#define HMC_MAX_ALLELES 16          /* alleles per locus (Amax) supported by the packed genotype / pair encoding */
+#define HMC_MAX_K       32          /* sample_size */
+
+/* hmc_get_counters slots */
+#define HMC_CNT_STEPS       0       /* (individual, locus) extensions that produced >= 1 state */
+#define HMC_CNT_STATES      1       /* sum of live states over all trellis indices (head included) */
+#define HMC_CNT_MAX_STATES  2       /* largest live-state set */
+#define HMC_CNT_ARRIVALS    3       /* addHaploPair calls (new state + merges), HaploBuilder.cpp:246 */
+#define HMC_CNT_WAVES       4       /* arena waves used by the last call */
+#define HMC_CNT_SPILL_STEPS 5       /* steps that left the shared-memory fast path */
+#define HMC_CNT_LAUNCHES    6       /* kernels launched by the last call */
+#define HMC_CNT_N           8
+
+/* Create a context on CUDA device `device`.  arena_bytes = 0 picks ~60% of free device memory for
+ * the trellis arena.  threads = 0 picks the threads-per-individual group size from the panel. */
+int hmc_ctx_create(hmc_ctx **out, int device, size_t arena_bytes, int threads);
+void hmc_ctx_destroy(hmc_ctx *ctx);
+const char *hmc_last_error(const hmc_ctx *ctx);
+/* version string of the loaded library, e.g. "hmc_b200 0.1 sm_100a" */
+const char *hmc_version(void);
+
+/* The panel: replaces HaploBuilder::setGenoData (HaploBuilder.h:47) + the GenoData allele tables
+ * (GenoData.h:43-49).  geno: [N][2][L] allele indices; n_alleles: [L]; allele_freq: [L][Amax].
+ * Genotypes are bit-packed on the device (K0). */
+int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, const int32_t *n_alleles, const double *allele_freq);
+
+/* The automaton: the HaploPattern fields HaploBuilder reads (HaploPattern.h:19-24,36-37) after
+ * PatternManager::initialize (PatternManager.cpp:293-318).  succ: [P][Amax], -1 = NULL successor;
+ * alleles: concatenated allele indices, al_off: [P+1]; heads: head_list ids in order
+ * (PatternManager.cpp:304-306). */
+int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const int32_t *end, const double *freq,
+                  const double *tp, const int32_t *succ, const int64_t *al_off, const int8_t *alleles, int n_heads, const int32_t *heads);
+
+/* HaploModel::resolveAll (HaploModel.cpp:79-115) over individuals [first, first+count) of the panel:
+ * one HaploBuilder::resolve (HaploBuilder.cpp:35-126) each, K = sample_size.
+ *   out_pg      [count]        genotype_probability (scaled by 2^out_exp when HMC_FLAG_SCALED)
+ *   out_exp     [count]        power-of-two exponent carried (0 without HMC_FLAG_SCALED)
+ *   out_cov     [count]        coverage returned by resolve()
+ *   out_nres    [count]        res_list.size()
+ *   out_prior   [count][K]     prior_probability of each entry, descending
+ *   out_post    [count][K]     posterior_probability
+ *   out_haps    [count][K][2][L] phased allele indices of each entry (may be NULL to skip the copy)
+ *   out_ll      [1]            sum of log P(G) over the range, in individual order
+ * Any out_* may be NULL.  Unresolvable individuals (no final state) get pg = 0, nres = 0. */
+int hmc_resolve_all(hmc_ctx *ctx, int first, int count, int K, unsigned flags, double *out_pg, int32_t *out_exp, double *out_cov,
+                    int32_t *out_nres, double *out_prior, double *out_post, int8_t *out_haps, double *out_ll);
+
+/* Device-resident variant used for kernel-only timing: runs the same kernels, leaves the results
+ * in device buffers owned by the context; hmc_fetch_results copies them out afterwards. */
+int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned flags);
+int hmc_fetch_results(hmc_ctx *ctx, double *out_pg, int32_t *out_exp, double *out_cov, int32_t *out_nres, double *out_prior,
+                      double *out_post, int8_t *out_haps, double *out_ll);
+
+/* HaploBuilder::estimateFrequency(vector<HaploPattern*>&) (HaploBuilder.cpp:274-332): expected
+ * pattern counts over individuals [first, first+count) for an explicit candidate list (which may
+ * hold patterns absent from the automaton, PatternManager.cpp:377-388).
+ *   start [Pc], al_off [Pc+1], alleles: the candidates
+ *   pg [count], pg_exp [count] (may be NULL = 0): genotype_probability from the preceding resolve_all
+ *   out_freq / out_prefix [Pc]: RAW sums over the range (before the normalisation of
+ *   HaploBuilder.cpp:317-331), so shards can be added (ncclAllReduce) before hmc_normalise_counts. */
+int hmc_estimate_counts(hmc_ctx *ctx, int first, int count, unsigned flags, int Pc, const int32_t *start, const int64_t *al_off,
+                        const int8_t *alleles, const double *pg, const int32_t *pg_exp, double *out_freq, double *out_prefix);
+/* Same, but the raw sums stay on the device: *dev_counts receives a device pointer to 2*Pc doubles
+ * (freq then prefix) owned by the context, for an in-place NCCL all-reduce. */
+int hmc_estimate_counts_device(hmc_ctx *ctx, int first, int count, unsigned flags, int Pc, const int32_t *start, const int64_t *al_off,
+                               const int8_t *alleles, const double *pg, const int32_t *pg_exp, double **dev_counts);
+/* HaploBuilder.cpp:317-331 on host arrays: clamp to N, freq <= prefix, divide by N, transition probability. */
+void hmc_normalise_counts(int Pc, int N, double *freq, double *prefix, double *tp);
+
+/* Structural counters of the last resolve/estimate call (HMC_CNT_*), for parity and the roofline. */
+int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N]);
+/* Device time (ms, CUDA events) of the kernels of the last call: [0] forward, [1] traceback, [2] backward, [3] E-step. */
+int hmc_get_kernel_ms(hmc_ctx *ctx, float out[4]);
+
+/* Parity hook: per-index live-state sets of one individual from the trellis kept by
+ * HMC_FLAG_KEEP_TRELLIS.  counts: [L+1]; the other arrays are concatenated over indices and must
+ * hold `capacity` entries; returns the total number of states or a negative status. */
+int64_t hmc_get_trellis(hmc_ctx *ctx, int individual, int32_t *counts, int64_t capacity, int32_t *ida, int32_t *idb, double *alpha,
+                        double *beta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMC_B200_H */
