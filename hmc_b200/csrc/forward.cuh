@@ -23,19 +23,19 @@ namespace hmc {
 template <int NT>
 struct BlockScan {
     // exclusive prefix sum over the block in thread order; total returned to every thread
-    __device__ static int run(int v, int &total, int *s_tmp)
+    __device__ static long long run(long long v, long long &total, long long *s_tmp)
     {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int x = v;
+        long long x = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         if (NT == 32) { total = __shfl_sync(0xffffffffu, x, 31); return x - v; }
         __syncthreads();            // protect s_tmp from the previous use
         if (lane == 31) s_tmp[wid] = x;
         __syncthreads();
-        int base = 0, tot = 0;
+        long long base = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { int t = s_tmp[w]; if (w < wid) base += t; tot += t; }
+        for (int w = 0; w < NT / 32; ++w) { long long t = s_tmp[w]; if (w < wid) base += t; tot += t; }
         total = tot;
         return base + x - v;
     }
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
     int *s_gx = s_idb + 2 * CC;                             // [MAX_GROUPS]
     int *s_gy = s_gx + MAX_GROUPS;
     int *s_gbase = s_gy + MAX_GROUPS;                       // [MAX_GROUPS+1]
-    int *s_tmp = s_gbase + MAX_GROUPS + 1;                  // [32] scan scratch
     __shared__ long long s_ll[4];                           // work item, alloc result, chunk cursor/end
+    __shared__ long long s_tmp[8];                          // scan scratch
     __shared__ int s_int[4];
 
     const int tid = threadIdx.x;
@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
     const DevModel &md = p.model;
     const int L = pn.L, A = md.Amax, K = p.K, head_len = md.head_len;
     const Scratch sc = p.scratch[blockIdx.x];
+    double *const sc_like0 = sc.like[0], *const sc_like1 = sc.like[1];
+    u64 *const sc_meta0 = sc.meta[0], *const sc_meta1 = sc.meta[1];
     u64 *const arena = p.arena.base;
 
     if (tid == 0) { s_ll[2] = 0; s_ll[3] = 0; }
@@ -206,8 +208,8 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
                 t_ab[s] = (unsigned char) (md.last[a] | (md.last[b] << 4));
                 if (p.estep) t_tp[s] = f;
                 else t_bp[(size_t) s * K] = BP_HEAD | (a == b ? BP_HOM : 0u);
-                sc.like[0][(size_t) s * K] = f;
-                sc.meta[0][s] = 1ull | ((a == b ? 1ull : 0ull) << 8);
+                sc_like0[(size_t) s * K] = f;
+                sc_meta0[s] = 1ull | ((a == b ? 1ull : 0ull) << 8);
             }
             if (tid == 0) { rec[head_len].off = cur_off; rec[head_len].count = S_in; }
         }
@@ -250,10 +252,10 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
             const bool in_cache = S_in <= CC;
             const int *ci_ida = s_ida + par * CC, *ci_idb = s_idb + par * CC;
             const double *ci_alpha = s_alpha + par * CC;
-            const double *like_in = sc.like[par];
-            const u64 *meta_in = sc.meta[par];
-            double *like_out = sc.like[par ^ 1];
-            u64 *meta_out = sc.meta[par ^ 1];
+            const double *like_in = par ? sc_like1 : sc_like0;
+            const u64 *meta_in = par ? sc_meta1 : sc_meta0;
+            double *like_out = par ? sc_like0 : sc_like1;
+            u64 *meta_out = par ? sc_meta0 : sc_meta1;
 
             // forward-link block of index i (E-step mode)
             long long fwd_off = 0;
@@ -306,46 +308,37 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
             }
             block_sync<NT>();
 
-            // ---- pass B: creators in ordinal order -> new state indices ----
-            int S_out = 0;
+            // ---- pass B+C: creators in ordinal order -> new state indices and arrival-segment offsets ----
+            int S_out = 0, n_arr = 0;
             for (int base = 0; base < C; base += NT) {
                 const int c = base + tid;
-                int creator = 0, h = 0;
+                int creator = 0, h = 0, n = 0;
                 if (c < C) {
                     const int enc = v.cand[c];
-                    if (enc >= 0) { h = enc & 0x3FFFFFFF; creator = (v.ord[h] == (u32) c); }
+                    if (enc >= 0) { h = enc & 0x3FFFFFFF; creator = (v.ord[h] == (u32) c); if (creator) n = (int) v.cnt[h]; }
                 }
-                int tot;
-                const int idx = S_out + BlockScan<NT>::run(creator, tot, s_tmp);
+                // one scan for both: creators in the high half, arrivals in the low half (C < 2^24 slots)
+                long long tot;
+                const long long ex = BlockScan<NT>::run(((long long) creator << 32) | (long long) n, tot, s_tmp);
                 if (creator) {
-                    v.ord[h] = 0x80000000u | (u32) idx;     // never equals a later ordinal
-                    v.slot_of[idx] = h;
+                    const int idx = S_out + (int) (ex >> 32);
+                    if (idx < sc.scap) {
+                        v.ord[h] = 0x80000000u | (u32) idx;     // never equals a later ordinal
+                        v.slot_of[idx] = h;
+                        v.aoff[idx] = n_arr + (int) (ex & 0xFFFFFFFFll);
+                        v.cnt[h] = 0;
+                    }
                 }
-                S_out += tot;
+                S_out += (int) (tot >> 32);
+                n_arr += (int) (tot & 0xFFFFFFFFll);
             }
-            block_sync<NT>();
             if (S_out == 0) {   // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82
                 S_in = 0;
                 break;
             }
             if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; break; }
-            if (tid == 0) s_ll[1] = alloc(block_layout(S_out, K, p.estep).total);
-
-            // ---- pass C: arrival offsets ----
-            {
-                int run = 0;
-                for (int base = 0; base < S_out; base += NT) {
-                    const int idx = base + tid;
-                    int n = 0, h = 0;
-                    if (idx < S_out) { h = v.slot_of[idx]; n = (int) v.cnt[h]; }
-                    int tot;
-                    const int ex = run + BlockScan<NT>::run(n, tot, s_tmp);
-                    if (idx < S_out) { v.aoff[idx] = ex; v.cnt[h] = 0; }
-                    run += tot;
-                }
-                if (tid == 0) v.aoff[S_out] = run;
-                c_arr += run;
-            }
+            if (tid == 0) { s_ll[1] = alloc(block_layout(S_out, K, p.estep).total); v.aoff[S_out] = n_arr; }
+            c_arr += n_arr;
             block_sync<NT>();
             const long long new_off = s_ll[1];
             if (new_off < 0) { status = ST_NOMEM; break; }
@@ -390,28 +383,55 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
                 double alpha = 0.0;
                 double bl[KMAX];
                 u32 bb[KMAX];
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) { bl[k] = -1.0; bb[k] = 0; }
                 int nl_out = 0, xa = 0, ya = 0;
                 for (int j = 0; j < n; ++j) {
                     const int e = v.arr[a0 + j];
                     const u32 rev = (u32) e >> 31;
                     int g, s, dir;
                     decode(e & 0x7FFFFFFF, g, s, dir);
+                    const bool het = (s_gx[g] != s_gy[g]);
                     if (j == 0) { const int x = dir ? s_gy[g] : s_gx[g], y = dir ? s_gx[g] : s_gy[g]; xa = rev ? y : x; ya = rev ? x : y; }
+                    // the predecessor's whole list in one batch of independent loads (sorted descending)
+                    const u64 mt = meta_in[s];
+                    const int nl = (int) (mt & 0xFF);
+                    u32 hom = (u32) (mt >> 8);
+                    double x[KMAX];
+                    const double *lp = like_in + (size_t) s * K;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) x[k] = (k < nl) ? lp[k] : 0.0;
                     const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
                     const double term = __dmul_rn(ain, tpv);
                     alpha = (j == 0) ? term : __dadd_rn(alpha, term);
-                    const u64 mt = meta_in[s];
-                    const int nl = (int) (mt & 0xFF);
-                    const u32 hom = (u32) (mt >> 8);
                     nl_out += nl;
-                    const bool het = (s_gx[g] != s_gy[g]);
-                    for (int k = 0; k < nl; ++k) {
-                        double lv = __dmul_rn(like_in[(size_t) s * K + k], tpv);
-                        u32 hk = (hom >> k) & 1u;
-                        if (het && hk) { if (rev) lv = 0.0; hk = 0; }
-                        if (lv > bl[KMAX - 1]) topk_insert<KMAX>(bl, bb, lv, (u32) s | ((u32) k << BP_PRED_BITS) | (rev ? BP_REV : 0u) | (hk ? BP_HOM : 0u));
+                    // het-locus rule (HaploPair.cpp:53-60,77-84): links still flagged homozygous lose the flag, and are
+                    // zeroed when this arrival is reversed
+                    const u32 zero = (het && rev) ? hom : 0u;
+                    if (het) hom = 0;
+                    const u32 bpbase = (u32) s | (rev ? BP_REV : 0u);
+                    if (j == 0 && zero == 0) {
+                        // scaling keeps the order: the first arrival's list is the initial top-K as it stands
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            bl[k] = (k < nl) ? __dmul_rn(x[k], tpv) : -1.0;
+                            bb[k] = bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u);
+                        }
+                    }
+                    else {
+                        if (j == 0) {
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) { bl[k] = -1.0; bb[k] = 0; }
+                        }
+                        // sorted input: stop at the first element that does not make the list (zeroed ones are retried)
+                        int k = 0;
+                        while (k < nl) {
+                            double lv = __dmul_rn(x[0], tpv);
+                            if ((zero >> k) & 1u) lv = 0.0;
+                            if (lv > bl[KMAX - 1]) topk_insert<KMAX>(bl, bb, lv, bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u));
+                            else if (zero == 0) break;
+#pragma unroll
+                            for (int q = 0; q + 1 < KMAX; ++q) x[q] = x[q + 1];
+                            ++k;
+                        }
                     }
                 }
                 if (nl_out > K) nl_out = K;
@@ -474,10 +494,10 @@ __global__ void __launch_bounds__(NT) forward_kernel(FwdParams p)
                 double *fl = (double *) (arena + fo);
                 u64 *fm = arena + fo + (long long) S_in * K;
                 for (int s = tid; s < S_in; s += NT) {
-                    const u64 mt = sc.meta[par][s];
+                    const u64 mt = (par ? sc_meta1 : sc_meta0)[s];
                     fm[s] = mt;
                     const int nl = (int) (mt & 0xFF);
-                    for (int k = 0; k < nl; ++k) fl[(size_t) s * K + k] = sc.like[par][(size_t) s * K + k];
+                    for (int k = 0; k < nl; ++k) fl[(size_t) s * K + k] = (par ? sc_like1 : sc_like0)[(size_t) s * K + k];
                 }
                 if (tid == 0) { rec[0].off = fo; rec[0].count = S_in; }     // index 0 is unused by the trellis when head_len >= 1
             }
