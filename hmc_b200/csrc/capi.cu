@@ -58,8 +58,8 @@ struct hmc_ctx {
     // panel
     int N = 0, L = 0, Amax = 0, bits = 0, words = 0;
     double missing_frac = 0;
-    DevBuf<u32> d_packed, d_amask;
-    DevBuf<int> d_nall, d_order;
+    DevBuf<u32> d_packed, d_linfo;
+    DevBuf<int> d_order;
     std::vector<int> h_order, h_rank;
     std::vector<int> h_nall;
 
@@ -67,6 +67,7 @@ struct hmc_ctx {
     bool have_model = false;
     DevModel dm = {};
     DevBuf<int> d_succ, d_start, d_heads, d_head_lut;
+    DevBuf<int4> d_succ16;
     DevBuf<double> d_tp, d_freq;
     DevBuf<unsigned char> d_last;
     DevBuf<long long> d_al_off;
@@ -80,6 +81,7 @@ struct hmc_ctx {
     DevBuf<long long> d_counters;
     DevBuf<LocusRec> d_loci;
     DevBuf<int> d_wave, d_status, d_final_exp, d_locus_exp;
+    DevBuf<long long> d_cycles;
     std::vector<int> h_wave;                 // last wave (for hmc_get_trellis)
     int last_K = 0, last_estep = 0;
     ScratchPool pool, big_pool;
@@ -131,11 +133,11 @@ __global__ void pack_kernel(const signed char *geno, int N, int L, int bits, int
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NT, int CC, int KMAX>
+template <int NT, int CC, int CL, int KMAX>
 static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
 {
-    auto kern = forward_kernel<NT, CC, KMAX>;
-    const size_t smem = forward_smem_bytes<CC>();
+    auto kern = forward_kernel<NT, CC, CL, KMAX>;
+    const size_t smem = sizeof(FwdSmem<NT, CC, CL, KMAX>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, NT, smem);
@@ -143,25 +145,25 @@ static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-template <int NT, int CC>
+template <int NT, int CC, int CL>
 static cudaError_t launch_forward_k(int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
 {
     switch (kmax) {
-        case 1: return launch_forward_t<NT, CC, 1>(p, grid, st, occ);
-        case 4: return launch_forward_t<NT, CC, 4>(p, grid, st, occ);
-        case 10: return launch_forward_t<NT, CC, 10>(p, grid, st, occ);
-        case 16: return launch_forward_t<NT, CC, 16>(p, grid, st, occ);
-        default: return launch_forward_t<NT, CC, 32>(p, grid, st, occ);
+        case 1: return launch_forward_t<NT, CC, CL, 1>(p, grid, st, occ);
+        case 4: return launch_forward_t<NT, CC, CL, 4>(p, grid, st, occ);
+        case 10: return launch_forward_t<NT, CC, CL, 10>(p, grid, st, occ);
+        case 16: return launch_forward_t<NT, CC, CL, 16>(p, grid, st, occ);
+        default: return launch_forward_t<NT, CC, CL / 2, 32>(p, grid, st, occ);
     }
 }
 
 static cudaError_t launch_forward(int nt, int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
 {
     switch (nt) {
-        case 32: return launch_forward_k<32, 128>(kmax, p, grid, st, occ);
-        case 64: return launch_forward_k<64, 256>(kmax, p, grid, st, occ);
-        case 128: return launch_forward_k<128, 512>(kmax, p, grid, st, occ);
-        default: return launch_forward_k<256, 1024>(kmax, p, grid, st, occ);
+        case 32: return launch_forward_k<32, 128, 64>(kmax, p, grid, st, occ);
+        case 64: return launch_forward_k<64, 256, 96>(kmax, p, grid, st, occ);
+        case 128: return launch_forward_k<128, 512, 128>(kmax, p, grid, st, occ);
+        default: return launch_forward_k<256, 1024, 256>(kmax, p, grid, st, occ);
     }
 }
 
@@ -188,7 +190,7 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
     const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_s = al((size_t) (scap + 1) * 4);
     const size_t b_like = al((size_t) scap * K * 8), b_meta = al((size_t) scap * 8);
-    const size_t per = b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 2 * b_meta;
+    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 2 * b_meta;
     CK(pl.mem.ensure(per * slots));
     CK(pl.desc.ensure(slots));
     std::vector<Scratch> h(slots);
@@ -197,6 +199,7 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
         Scratch &s = h[i];
         s.hcap = hcap; s.ccap = ccap; s.scap = scap;
         s.keys = (u64 *) b; b += b_keys;
+        s.tpv = (double *) b; b += b_keys;
         s.ord = (u32 *) b; b += b_u32;
         s.cnt = (u32 *) b; b += b_u32;
         s.nidx = nullptr;
@@ -253,8 +256,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     if (rc) return rc;
     CK(ctx->d_cursor.ensure(1));
     CK(ctx->d_flags.ensure(2));
-    CK(ctx->d_counters.ensure(8));
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(long long), ctx->stream));
+    CK(ctx->d_counters.ensure(24));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 24 * sizeof(long long), ctx->stream));
     memset(ctx->counters, 0, sizeof ctx->counters);
     memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
 
@@ -299,7 +302,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         CK(cudaMemsetAsync(ctx->d_status.p, 0, sizeof(int) * n_wave, ctx->stream));
 
         fp.panel.N = ctx->N; fp.panel.L = L; fp.panel.Amax = ctx->Amax; fp.panel.bits = ctx->bits; fp.panel.words = ctx->words;
-        fp.panel.packed = ctx->d_packed.p; fp.panel.nall = ctx->d_nall.p; fp.panel.amask = ctx->d_amask.p; fp.panel.order = ctx->d_order.p;
+        fp.panel.packed = ctx->d_packed.p; fp.panel.linfo = ctx->d_linfo.p; fp.panel.order = ctx->d_order.p;
         fp.model = ctx->dm;
         fp.arena.base = ctx->d_arena.p; fp.arena.capacity = (long long) ctx->d_arena.n; fp.arena.cursor = ctx->d_cursor.p; fp.arena.exhausted = ctx->d_flags.p;
         fp.scratch = pl.desc.p;
@@ -308,6 +311,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         fp.status = ctx->d_status.p; fp.final_exp = ctx->d_final_exp.p;
         fp.locus_exp = (estep && fp.scaled) ? ctx->d_locus_exp.p : nullptr;
         fp.queue = ctx->d_flags.p + 1; fp.counters = ctx->d_counters.p;
+        fp.ind_cycles = nullptr;
+        if (getenv("HMC_B200_DEBUG_CYCLES")) { CK(ctx->d_cycles.ensure(wave_cap)); CK(cudaMemsetAsync(ctx->d_cycles.p, 0, sizeof(long long) * n_wave, ctx->stream)); fp.ind_cycles = ctx->d_cycles.p; }
 
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         CK(launch_forward(nt, kmax, fp, slots, ctx->stream, nullptr));
@@ -352,8 +357,12 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         pending.erase(pending.begin(), pending.begin() + n_wave);
         pending.insert(pending.begin(), again.begin(), again.end());
     }
-    long long hc[8];
+    long long hc[24];
     CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+    if (getenv("HMC_B200_PRINT_PASSES"))
+        for (int b = 8; b < 24; b += 8)
+            fprintf(stderr, "%s pass Mcycles: clear %lld  A %lld  BC %lld  D %lld  E %lld  tail %lld  pre %lld | slots %lld\n", b == 8 ? "fast " : "spill",
+                    hc[b] >> 20, hc[b + 1] >> 20, hc[b + 2] >> 20, hc[b + 3] >> 20, hc[b + 4] >> 20, hc[b + 5] >> 20, hc[b + 7] >> 20, hc[b + 6]);
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
@@ -389,7 +398,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_packed.release(); ctx->d_amask.release(); ctx->d_nall.release(); ctx->d_order.release();
+    ctx->d_packed.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
     ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
@@ -420,6 +429,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     for (int l = 0; l < L; ++l) {
         if (n_alleles[l] < 0 || n_alleles[l] > Amax) return ctx->fail(HMC_ERR_INVALID, "n_alleles[%d] = %d outside [0,%d]", l, n_alleles[l], Amax);
         for (int j = 0; j < n_alleles[l]; ++j) if (allele_freq[(size_t) l * Amax + j] > 0) amask[l] |= 1u << j;
+        amask[l] = (u32) n_alleles[l] | (amask[l] << 8);
     }
     std::vector<int> miss(N, 0);
     size_t tot_miss = 0;
@@ -437,14 +447,12 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     for (int i = 0; i < N; ++i) ctx->h_order[i] = i;
     std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) { return miss[a] > miss[b]; });
     CK(ctx->d_packed.ensure((size_t) N * ctx->words));
-    CK(ctx->d_amask.ensure(L));
-    CK(ctx->d_nall.ensure(L));
+    CK(ctx->d_linfo.ensure(L));
     CK(ctx->d_order.ensure(N));
     DevBuf<signed char> raw;
     CK(raw.ensure((size_t) N * 2 * L));
     CK(cudaMemcpyAsync(raw.p, geno, (size_t) N * 2 * L, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_amask.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_nall.p, n_alleles, sizeof(int) * L, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_linfo.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
     const size_t nthr = (size_t) N * ctx->words;
     pack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, ctx->stream>>>(raw.p, N, L, ctx->bits, ctx->words, ctx->d_packed.p);
@@ -480,6 +488,18 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
         for (int j = 0; j < head_len; ++j) code += (long long) alleles[al_off[id] + j] * stride[j];
         lut[(size_t) code] = id;
     }
+    // 16-byte successor entries: one 128-bit gather yields the successor and its transition probability
+    std::vector<int4> s16((size_t) P * A);
+    for (size_t q = 0; q < (size_t) P * A; ++q) {
+        const int id = succ[q];
+        if (id >= P) return ctx->fail(HMC_ERR_INVALID, "successor id out of range");
+        const double t = id >= 0 ? tp[id] : 0.0;
+        long long bits;
+        memcpy(&bits, &t, 8);
+        s16[q] = make_int4(id, 0, (int) (bits & 0xFFFFFFFFll), (int) (bits >> 32));
+    }
+    CK(ctx->d_succ16.ensure((size_t) P * A));
+    CK(cudaMemcpyAsync(ctx->d_succ16.p, s16.data(), sizeof(int4) * (size_t) P * A, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_succ.ensure((size_t) P * A)); CK(ctx->d_start.ensure(P)); CK(ctx->d_tp.ensure(P)); CK(ctx->d_freq.ensure(P)); CK(ctx->d_last.ensure(P));
     CK(ctx->d_al_off.ensure(P + 1)); CK(ctx->d_al.ensure((size_t) al_off[P] + 1)); CK(ctx->d_heads.ensure(std::max(1, n_heads))); CK(ctx->d_head_lut.ensure(lut.size()));
     cudaStream_t st = ctx->stream;
@@ -495,7 +515,7 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     CK(cudaStreamSynchronize(st));
     DevModel &m = ctx->dm;
     m.P = P; m.head_len = head_len; m.n_heads = n_heads; m.Amax = A;
-    m.succ = ctx->d_succ.p; m.tp = ctx->d_tp.p; m.freq = ctx->d_freq.p; m.start = ctx->d_start.p; m.last = ctx->d_last.p;
+    m.succ = ctx->d_succ.p; m.succ16 = ctx->d_succ16.p; m.tp = ctx->d_tp.p; m.freq = ctx->d_freq.p; m.start = ctx->d_start.p; m.last = ctx->d_last.p;
     m.al_off = ctx->d_al_off.p; m.al = ctx->d_al.p; m.heads = ctx->d_heads.p; m.head_lut = ctx->d_head_lut.p;
     for (int j = 0; j < 8; ++j) m.head_stride[j] = stride[j];
     ctx->have_model = true;
@@ -568,6 +588,16 @@ int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N])
     if (!ctx || !out) return HMC_ERR_INVALID;
     memcpy(out, ctx->counters, sizeof ctx->counters);
     return HMC_OK;
+}
+
+// diagnostics (HMC_B200_DEBUG_CYCLES=1): SM cycles per individual of the last wave, in wave order; returns the count
+int hmc_debug_cycles(hmc_ctx *ctx, long long *out, int *inds, int cap)
+{
+    if (!ctx || !ctx->d_cycles.p) return 0;
+    const int n = std::min<int>(cap, (int) ctx->h_wave.size());
+    cudaMemcpy(out, ctx->d_cycles.p, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i) inds[i] = ctx->h_wave[i];
+    return n;
 }
 
 int hmc_get_kernel_ms(hmc_ctx *ctx, float out[4])

@@ -31,8 +31,7 @@ struct DevPanel {
     int bits;                   // bits per allele code (code = index + 1, 0 = missing): 2, 4 or 8
     int words;                  // 32-bit words per individual
     const u32 *packed;          // [N][words]
-    const int *nall;            // [L]
-    const u32 *amask;           // [L] bit j set <=> allele_frequency(l, j) > 0
+    const u32 *linfo;           // [L] allele_num(l) | mask << 8, mask bit j set <=> allele_frequency(l, j) > 0
     const int *order;           // [N] work order (heaviest individuals first)
 };
 
@@ -40,6 +39,7 @@ struct DevPanel {
 struct DevModel {
     int P, head_len, n_heads, Amax;
     const int *succ;            // [P][Amax]
+    const void *succ16;         // [P][Amax] 16-byte entries {int successor id; int pad; double transition_prob of the successor}
     const double *tp;           // [P] transition_prob
     const double *freq;         // [P] frequency
     const int *start;           // [P]
@@ -72,6 +72,7 @@ struct Arena {
 struct Scratch {
     int hcap, ccap, scap;       // hash slots (power of two), candidate slots, states
     u64 *keys;                  // [hcap]
+    double *tpv;                // [hcap] transition-probability product of the slot's state
     u32 *ord, *cnt, *nidx;      // [hcap]
     int *cand, *arr;            // [ccap]
     int *aoff, *slot_of;        // [scap+1], [scap]
@@ -95,6 +96,7 @@ struct FwdParams {
     int *locus_exp;             // [n_wave][L+1] cumulative exponent (scaled mode, E-step) or null
     int *queue;                 // work-queue head
     long long *counters;        // steps, states, max_states, arrivals, -, spill steps
+    long long *ind_cycles;      // [n_wave] SM clock cycles spent on each individual (diagnostics) or null
 };
 
 // trellis state-block layout (units of 8 bytes) for S states
