@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "forward.cuh"
+#include "forward_warp.cuh"
 #include "traceback.cuh"
 #include "estep.cuh"
 
@@ -157,10 +158,34 @@ static cudaError_t launch_forward_k(int kmax, const FwdParams &p, int grid, cuda
     }
 }
 
+template <int CS, int CL, int KMAX>
+static cudaError_t launch_warp_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
+{
+    auto kern = forward_warp_kernel<CS, CL, KMAX>;
+    const size_t smem = sizeof(WarpSmem<CS, CL, KMAX>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, 32, smem);
+    kern<<<grid, 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_warp(int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
+{
+    switch (kmax) {
+        case 1: return launch_warp_t<256, 256, 1>(p, grid, st, occ);
+        case 4: return launch_warp_t<256, 128, 4>(p, grid, st, occ);
+        case 10: return launch_warp_t<256, 64, 10>(p, grid, st, occ);
+        case 16: return launch_warp_t<256, 48, 16>(p, grid, st, occ);
+        default: return launch_warp_t<256, 32, 32>(p, grid, st, occ);
+    }
+}
+
 static cudaError_t launch_forward(int nt, int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
 {
     switch (nt) {
-        case 32: return launch_forward_k<32, 128, 64>(kmax, p, grid, st, occ);
+        case 32: return launch_warp(kmax, p, grid, st, occ);
+        case 33: return launch_forward_k<32, 128, 64>(kmax, p, grid, st, occ);
         case 64: return launch_forward_k<64, 256, 96>(kmax, p, grid, st, occ);
         case 128: return launch_forward_k<128, 512, 128>(kmax, p, grid, st, occ);
         default: return launch_forward_k<256, 1024, 256>(kmax, p, grid, st, occ);
@@ -190,7 +215,8 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
     const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_s = al((size_t) (scap + 1) * 4);
     const size_t b_like = al((size_t) scap * K * 8), b_meta = al((size_t) scap * 8);
-    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 2 * b_meta;
+    const size_t b_obp = al((size_t) scap * K * 4);
+    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 3 * b_meta + b_obp;
     CK(pl.mem.ensure(per * slots));
     CK(pl.desc.ensure(slots));
     std::vector<Scratch> h(slots);
@@ -211,6 +237,8 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
         s.like[1] = (double *) b; b += b_like;
         s.meta[0] = (u64 *) b; b += b_meta;
         s.meta[1] = (u64 *) b; b += b_meta;
+        s.otp = (double *) b; b += b_meta;
+        s.obp = (u32 *) b; b += b_obp;
     }
     CK(cudaMemcpyAsync(pl.desc.p, h.data(), sizeof(Scratch) * slots, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -237,8 +265,8 @@ static int pick_threads(const hmc_ctx *ctx)
 {
     const char *env = getenv("HMC_B200_THREADS");
     int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
-    if (nt == 0) nt = ctx->missing_frac > 0.02 ? 128 : (ctx->missing_frac > 0.002 ? 64 : 32);
-    if (nt != 32 && nt != 64 && nt != 128 && nt != 256) nt = 128;
+    if (nt == 0) nt = ctx->missing_frac > 0.02 ? 256 : 128;
+    if (nt != 32 && nt != 33 && nt != 64 && nt != 128 && nt != 256) nt = 128;
     return nt;
 }
 
@@ -361,7 +389,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
     if (getenv("HMC_B200_PRINT_PASSES"))
         for (int b = 8; b < 24; b += 8)
-            fprintf(stderr, "%s pass Mcycles: clear %lld  A %lld  BC %lld  D %lld  E %lld  tail %lld  pre %lld | slots %lld\n", b == 8 ? "fast " : "spill",
+            fprintf(stderr, "%s pass Mcycles: [0] %lld  [1] %lld  [2] %lld  [3] %lld  [4] %lld  [5] %lld  [7] %lld | [6] %lld\n", b == 8 ? "fast " : "spill",
                     hc[b] >> 20, hc[b + 1] >> 20, hc[b + 2] >> 20, hc[b + 3] >> 20, hc[b + 4] >> 20, hc[b + 5] >> 20, hc[b + 7] >> 20, hc[b + 6]);
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5];

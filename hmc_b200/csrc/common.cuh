@@ -73,6 +73,8 @@ struct Scratch {
     int hcap, ccap, scap;       // hash slots (power of two), candidate slots, states
     u64 *keys;                  // [hcap]
     double *tpv;                // [hcap] transition-probability product of the slot's state
+    double *otp;                // [scap] warp kernel: transition probability of spilled output states
+    u32 *obp;                   // [scap*K] warp kernel: back-pointer words of spilled output states
     u32 *ord, *cnt, *nidx;      // [hcap]
     int *cand, *arr;            // [ccap]
     int *aoff, *slot_of;        // [scap+1], [scap]
