@@ -96,7 +96,6 @@ struct hmc_ctx {
     // E-step
     DevBuf<double> d_counts, d_pgin;
     DevBuf<int> d_pgexp;
-    EstepTrie trie;
 
     int64_t counters[HMC_CNT_N] = {};
     float kernel_ms[4] = {};
@@ -434,7 +433,6 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
     ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
-    ctx->trie.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
