@@ -1,4 +1,6 @@
 """hmc_b200 -- B200-native HaploBuilder / EM E-step path of HMC."""
 from .device import DeviceBuilder, HmcError, FLAG_SCALED, FLAG_KEEP_TRELLIS  # noqa: F401
 
-__all__ = ["DeviceBuilder", "HmcError", "FLAG_SCALED", "FLAG_KEEP_TRELLIS"]
+from .host import HaploModel  # noqa: F401,E402
+
+__all__ = ["HaploModel", "DeviceBuilder", "HmcError", "FLAG_SCALED", "FLAG_KEEP_TRELLIS"]

@@ -20,6 +20,24 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(os.path.dirname(HERE), "include", "hmc_b200.h")]
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_SO = os.path.join(HERE, "libhmc_host.so")
+CLI = os.path.join(HERE, "bin", "hmc")
+
+
+def build_host(force: bool = False) -> str:
+    """libhmc_host.so (host classes + flat C API) and bin/hmc (the CLI); both link libhmc_b200.so next to them."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("hmc_host.cpp", "hmc_host.hpp", "host_capi.cpp", "hmc_cli.cpp")]
+    cxx = os.environ.get("CXX", "g++")
+    flags = ["-std=c++17", "-O3", "-fPIC", "-pthread", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
+    if force or not os.path.exists(HOST_SO) or any(os.path.getmtime(s) > os.path.getmtime(HOST_SO) for s in srcs + [SO]):
+        subprocess.check_call([cxx] + flags + ["-shared", "-o", HOST_SO, srcs[0], srcs[2], "-L" + HERE, "-lhmc_b200", "-Wl,-rpath,$ORIGIN"])
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    if force or not os.path.exists(CLI) or any(os.path.getmtime(s) > os.path.getmtime(CLI) for s in srcs + [SO]):
+        subprocess.check_call([cxx] + flags + ["-o", CLI, srcs[0], srcs[3], "-L" + HERE, "-lhmc_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return HOST_SO
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     if not force and os.path.exists(SO) and all(os.path.getmtime(s) <= os.path.getmtime(SO) for s in srcs):
@@ -33,3 +51,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -78,7 +78,8 @@ class DeviceBuilder:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().hmc_ctx_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().hmc_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -1,0 +1,87 @@
+"""CPU: the host layer (PHASE I/O, mining, automaton) against the reference dumps; the C-ABI library's exports."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from hmc_b200.device import EXPORTS, library_path
+from hmc_b200.host import HaploModel
+from util import GOLDEN, golden, model_opts
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_phase_reader_and_first_model(name):
+    d = golden(name)
+    hm = HaploModel(**model_opts(name))
+    hm.load_phase(os.path.join(GOLDEN, name + ".phase"))
+    idx, na, af = hm.panel()
+    assert np.array_equal(idx, d["geno"]) and np.array_equal(na, d["nall"]) and np.array_equal(af, d["afreq"])
+    hm.build()          # mining + automaton only: no device needed until the first resolve
+    m, r = hm.export_model(), d["iters"][0]["patterns"]
+    assert m["P"] == r["P"] and m["head_len"] == r["head_len"]
+    for k in ("start", "end", "freq", "prefix", "tp", "succ", "heads"):
+        assert np.array_equal(m[k], r[k]), k
+    assert np.array_equal(np.concatenate(r["al"]), m["al"])
+    hm.close()
+
+
+def test_mining_is_thread_count_independent():
+    d = golden("g2_missing")
+    ms = []
+    for t in (1, 3, 8):
+        hm = HaploModel(host_threads=t)
+        hm.load_phase(os.path.join(GOLDEN, "g2_missing.phase"))
+        hm.build()
+        ms.append(hm.export_model())
+        hm.close()
+    for m in ms[1:]:
+        for k in ("start", "end", "freq", "prefix", "tp", "succ", "heads", "al"):
+            assert np.array_equal(m[k], ms[0][k]), k
+
+
+def test_set_panel_from_codes_equals_phase_file():
+    d = golden("g3_multi")
+    hm = HaploModel()
+    hm.set_panel(d["geno"], kind="M")       # codes == indices here only if every allele value occurs; compare through the tables
+    idx, na, af = hm.panel()
+    assert np.array_equal(na, d["nall"]) and np.array_equal(af, d["afreq"]) and np.array_equal(idx, d["geno"])
+    hm.close()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "hmc_b200.h")).read()
+    declared = set(re.findall(r"\b(hmc_[a-z_]+)\s*\(", hdr))
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    L = C.CDLL(library_path())
+    for name in declared:
+        assert hasattr(L, name), name
+    L.hmc_version.restype = C.c_char_p
+    assert b"sm_100a" in L.hmc_version()
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from hmc_b200 import DeviceBuilder, HmcError
+    with pytest.raises(HmcError):
+        DeviceBuilder()
+    hm = HaploModel()
+    hm.load_phase(os.path.join(GOLDEN, "g1_clean.phase"))
+    hm.build()
+    with pytest.raises(HmcError):
+        hm.resolve_all()
+    hm.close()
+
+
+def test_normalise_counts_matches_reference_rule():
+    from hmc_b200 import DeviceBuilder
+    f = np.array([0.0, 3.0, 50.0, 2.0, 1.0])
+    pf = np.array([0.0, 4.0, 45.0, 2.0, 0.5])
+    nf, npf, tp = DeviceBuilder.normalise_counts(f, pf, 40)
+    # HaploBuilder.cpp:317-331: clamp to N, freq <= prefix, /N, tp = freq/prefix (or freq/N), tp <= 1
+    assert np.allclose(nf, [0, 3 / 40, 1.0, 2 / 40, 0.5 / 40]) and np.allclose(npf, [0, 0.1, 1.0, 0.05, 0.0125])
+    assert np.allclose(tp, [0, 0.75, 1.0, 1.0, 1.0])
