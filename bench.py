@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- individual x locus phasing steps/sec per EM iteration (BASELINE.json).
+
+One "step" of the bench is one HaploModel::resolveAll pass (K1 forward + K2 traceback, sample-size 10)
+over this rank's shard of the synthetic C2 panel (2,000 individuals x 1,000 SNPs, 5 % missing
+genotypes, default HMC options); the metric counts individual x locus extensions per second.
+
+  python bench.py [--gpus N --steps K --warmup W]        our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                   the reference's own CPU implementation (oracle/_ref)
+
+`value`   = device-resident throughput (panel + model already in HBM, results left in HBM)
+`e2e`     = the same pass through the C-ABI with HOST buffers: panel + model H2D, results D2H every step
+`roofline`= algorithmic bytes of the forward kernel / its CUDA-event time vs the measured HBM copy peak
+`cpu_baseline` = the oracle port timed on a bounded sample of the same workload on this host (1 core)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2"            # SURVEY.md par. 8d: 2,000 x 1,000 biallelic, 16 founders, 5 % missing genotypes, seed 2
+K_SAMPLE = 10               # --sample-size default (HMC.cpp:44)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self) -> dict:
+        self._halt.set()
+        self.join(timeout=2)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def algorithmic_bytes(c: dict, K: int) -> float:
+    """SURVEY.md par. 8d: 24 B per arrival (2 x {succ id, transition prob}) + per new state ids, tp, alpha and K x (likelihood,
+    back-pointer) written + per predecessor state ids, alpha and K likelihoods read.  sum S_in ~ sum S_out ~ states."""
+    return 24.0 * c["arrivals"] + c["states"] * (24 + 16 * K) + c["states"] * (16 + 8 * K)
+
+
+def make_workload(n_gpus: int):
+    from hmc_b200.synth import CONFIGS, make_panel
+    N, L, A, F, m, seed, kind = CONFIGS[WORKLOAD]
+    n_ind = env_int("HMC_BENCH_N", N)
+    n_loci = env_int("HMC_BENCH_L", L)
+    g = make_panel(n_ind * n_gpus, n_loci, alleles=A, founders=F, missing=m, seed=seed)
+    return g, kind, n_ind, n_loci
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = max(world, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+
+    from hmc_b200 import HaploModel
+
+    g, kind, n_ind, n_loci = make_workload(n_gpus)
+    t0 = time.time()
+    hm = HaploModel(device=local, host_threads=max(1, (os.cpu_count() or 8) // n_gpus))
+    hm.set_panel(g, kind)               # the whole panel: the M-step (mining) is replicated on every rank
+    hm.build()
+    model = hm.export_model()
+    t_model = time.time() - t0
+    idx, n_alleles, allele_freq = hm.panel()
+    first = rank * n_ind                # this rank's shard of individuals (no data-path collective)
+    shard = np.ascontiguousarray(idx[first:first + n_ind])
+
+    # pinned host staging for the end-to-end leg
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    host = {}
+    for k, a in (("geno", shard), ("n_alleles", n_alleles), ("allele_freq", allele_freq)):
+        t, host[k] = pinned(a); keep.append(t)
+    hmodel = dict(model)
+    for k in ("start", "end", "freq", "tp", "succ", "al_off", "al", "heads"):
+        t, hmodel[k] = pinned(model[k]); keep.append(t)
+    h2d = sum(host[k].nbytes for k in host) + sum(hmodel[k].nbytes for k in ("start", "end", "freq", "tp", "succ", "al_off", "al", "heads"))
+
+    from hmc_b200 import DeviceBuilder
+    dev = DeviceBuilder(device=local)
+    dev.set_panel(host["geno"], host["n_alleles"], host["allele_freq"])
+    dev.set_model(hmodel)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ll_buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
+
+    def step_device():
+        dev.resolve_all_device(K=K_SAMPLE)
+        if world > 1:       # the per-iteration exchange of the sampling EM: one scalar (LL); samples go to the host for mining
+            dist.all_reduce(ll_buf)
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    fwd_ms, tb_ms, launches = [], [], 0
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+        ms = dev.kernel_ms()
+        fwd_ms.append(ms["forward"]); tb_ms.append(ms["traceback"])
+        launches += dev.counters()["launches"]
+    barrier()
+    elapsed = time.perf_counter() - t_begin
+    clocks = sampler.stop() if rank == 0 else None
+    counters = dev.counters()
+    steps_per_pass = counters["steps"]
+    dev_ms = float(np.mean(fwd_ms) + np.mean(tb_ms))        # CUDA-event time of the kernels of one pass (timed on their stream)
+
+    # ---- end to end through the C-ABI with host buffers ----
+    res = None
+    for _ in range(min(args.warmup, 2)):
+        dev.set_panel(host["geno"], host["n_alleles"], host["allele_freq"]); dev.set_model(hmodel)
+        res = dev.resolve_all(K=K_SAMPLE)
+    barrier()
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        dev.set_panel(host["geno"], host["n_alleles"], host["allele_freq"])
+        dev.set_model(hmodel)
+        res = dev.resolve_all(K=K_SAMPLE)
+    barrier()
+    e2e_elapsed = time.perf_counter() - t_begin
+    d2h = sum(res[k].nbytes for k in ("pg", "exp", "coverage", "nres", "prior", "posterior", "haps"))
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([elapsed, e2e_elapsed, dev_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, e2e_elapsed, dev_ms = [float(x) for x in t.tolist()]
+        s = torch.tensor([float(steps_per_pass)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(s)
+        total_steps = float(s.item())
+    else:
+        total_steps = float(steps_per_pass)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = elapsed / args.steps * 1e3
+    value = total_steps / (elapsed / args.steps)
+    e2e_value = total_steps / (e2e_elapsed / args.steps)
+    peak, peak_kind = peaks()
+    alg = algorithmic_bytes(counters, K_SAMPLE)
+    fwd_s = float(np.mean(fwd_ms)) * 1e-3
+    achieved = alg / fwd_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "forward_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    cpu = cpu_baseline(shard, n_alleles, allele_freq, model, n_loci)
+
+    line = {
+        "metric": "individual x locus phasing steps/sec per EM iteration", "value": value, "unit": "steps/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: {n_ind} individuals x {n_loci} SNPs per GPU, 5% missing genotypes, 16 founders, default HMC options "
+                               f"(MV, min-freq-abs 1.5, max-pattern-len 30, sample-size {K_SAMPLE})",
+                   "pass": "HaploModel::resolveAll = K1 forward + K2 traceback", "patterns": int(model["P"]), "steps_per_pass": int(total_steps),
+                   "mean_states": counters["states"] / max(counters["steps"], 1), "arrivals_per_step": counters["arrivals"] / max(counters["steps"], 1),
+                   "max_states": counters["max_states"], "l2": "trellis + model working set (GBs) exceeds the 126 MB L2; no flush needed",
+                   "model_build_s": t_model, "sharding": "individuals; model replicated; LL all-reduce only"},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "kernel_ms": {"forward": float(np.mean(fwd_ms)), "traceback": float(np.mean(tb_ms)), "device_total": dev_ms},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "forward (K1)", "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(shard, n_alleles, allele_freq, model, n_loci, target_s: float = 12.0) -> dict:
+    """The oracle port (oracle/hmc_oracle.hpp, single thread, same libstdc++ as the reference build) on the first individuals of the
+    shard with the SAME model: the reference binary would spend minutes mining before its first resolve at this size."""
+    try:
+        from oracle.pyoracle import Oracle
+        secs, steps = 0.0, 0
+        n_try = 4
+        while True:
+            o2 = Oracle(shard[:n_try], sample_size=K_SAMPLE)
+            o2.set_allele_table(n_alleles, allele_freq)     # the full panel's alleles and frequencies, not the sample's own
+            o2.import_model(model, min_len=1, max_len=30, min_freq=0.0)
+            t0 = time.perf_counter()
+            o2.resolve_all()
+            secs = time.perf_counter() - t0
+            steps = o2.counters()["steps"]
+            if secs >= target_s / 3 or n_try >= len(shard):
+                break
+            n_try = min(len(shard), max(n_try * 2, int(n_try * target_s / max(secs, 1e-3) * 0.6)))
+        return {"value": steps / secs, "unit": "steps/s", "cores": 1, "kind": "port",
+                "sample": f"first {n_try} individuals x {n_loci} loci of the same shard, same model, sample-size {K_SAMPLE}: {secs:.1f} s on one core"}
+    except Exception as e:      # the baseline is reported, never required
+        return {"value": None, "unit": "steps/s", "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref/hmc_ref, the unmodified sources) on the same workload, one process per host
+    core (the reference is single-threaded and non-reentrant); each step resolves a bounded sample of individuals per process."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    n_gpus = max(env_int("WORLD_SIZE", 1), 1)
+    from hmc_b200.synth import write_phase
+    g, kind, n_ind, n_loci = make_workload(1)
+    ref = os.path.join(ROOT, "oracle", "_ref", "hmc_ref")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/hmc_ref was not built (needs /root/reference at build time)"}))
+        return
+    tmp = os.environ.get("TMPDIR", "/tmp")
+    phase = os.path.join(tmp, f"hmc_bench_{WORKLOAD}_{n_ind}x{n_loci}.phase")
+    write_phase(phase, g, kind=kind)
+    cores = os.cpu_count() or 1
+    procs_n = max(1, min(cores, env_int("HMC_BENCH_REF_PROCS", 16), n_ind))
+    per = max(1, env_int("HMC_BENCH_REF_SAMPLE", 4))
+    cmds = []
+    for p in range(procs_n):
+        cmds.append([ref, phase, "--time-resolve", str(per), "--time-offset", str((p * per) % n_ind), "--time-steps", str(args.steps),
+                     "--time-warmup", str(min(args.warmup, 1)), "-d", "1"])
+    t0 = time.time()
+    procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for c in cmds]
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.time() - t0
+    steps_total, worst, build_s = 0, 0.0, 0.0
+    for o in outs:
+        try:
+            j = json.loads(o.strip().splitlines()[-1])
+        except Exception:
+            continue
+        steps_total += j["resolve_steps"]
+        worst = max(worst, float(np.mean(j["resolve_s"])))
+        build_s = max(build_s, j["build_s"])
+    if steps_total == 0 or worst <= 0:
+        print(json.dumps({"impl": "reference", "unavailable": "hmc_ref produced no timing"}))
+        return
+    value = steps_total / worst
+    sample = (f"{procs_n} processes x first-come slices of {per} individuals x {n_loci} loci of the C2 panel, full-panel model mined by each process "
+              f"({build_s:.0f} s, outside the timed region), sample-size {K_SAMPLE}; wall {wall:.0f} s")
+    line = {
+        "impl": "reference", "metric": "individual x locus phasing steps/sec per EM iteration", "value": value, "unit": "steps/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": worst * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: {n_ind} individuals x {n_loci} SNPs, 5% missing genotypes, 16 founders, default HMC options", "pass": "HaploModel::resolveAll"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": procs_n, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,16 @@ void orc_get_allele_table(void *p, int *nall, double *afreq)
     memcpy(nall, pn.nall.data(), sizeof(int) * pn.L);
     memcpy(afreq, pn.afreq.data(), sizeof(double) * pn.afreq.size());
 }
+// override the allele table (a sub-sample must keep the full panel's alleles and frequencies)
+void orc_set_allele_table(void *p, int Amax, const int *nall, const double *afreq)
+{
+    Handle *h = (Handle *) p;
+    for (Panel *pn : {&h->input, &h->hm.panel}) {
+        pn->Amax = Amax;
+        pn->nall.assign(nall, nall + pn->L);
+        pn->afreq.assign(afreq, afreq + (size_t) pn->L * Amax);
+    }
+}
 void orc_find_patterns(void *p) { Handle *h = (Handle *) p; h->hm.samples.clear(); h->hm.findPatterns(); }
 int orc_num_patterns(void *p) { return ((Handle *) p)->hm.model.P(); }
 int orc_head_len(void *p) { return ((Handle *) p)->hm.model.head_len(); }

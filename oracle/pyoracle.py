@@ -80,6 +80,12 @@ class Oracle:
         lib().orc_get_allele_table(self._h, _p(nall), _p(afreq))
         return nall, afreq
 
+    def set_allele_table(self, nall, afreq):
+        nall = np.ascontiguousarray(nall, np.int32)
+        afreq = np.ascontiguousarray(afreq, np.float64)
+        self.Amax = afreq.shape[1]
+        lib().orc_set_allele_table(self._h, C.c_int(self.Amax), _p(nall), _p(afreq))
+
     def find_patterns(self):
         lib().orc_find_patterns(self._h)
 

@@ -31,7 +31,7 @@ static double now_s()
 struct DriverOpts {
 	string input, dump, out_suffix;
 	bool dump_states = false, dump_beta = false, dump_estep = false, dump_patterns = true, dump_klist = true;
-	int time_resolve = 0, time_estep = 0;
+	int time_resolve = 0, time_estep = 0, time_offset = 0, time_steps = 1, time_warmup = 0;
 	DriverOpts() : out_suffix(".reconstructed") {}
 };
 
@@ -212,15 +212,23 @@ public:
 		int head_len = m_patterns.head_len();
 		printf("{\"build_s\": %.6f, \"patterns\": %d, \"N\": %d, \"L\": %d", t_build, pattern_num(), genos.genotype_num(), genos.genotype_len());
 		if (opt.time_resolve > 0) {
-			int n = min(opt.time_resolve, genos.genotype_num());
+			// sub-panel = individuals [offset, offset+n) of the full panel, allele tables and model of the full panel
+			int off = min(opt.time_offset, genos.genotype_num() - 1);
+			int n = min(opt.time_resolve, genos.genotype_num() - off);
 			GenoData sub = unphased;
+			for (int i = 0; i < n; ++i) sub[i] = unphased[off + i];
 			sub.setGenotypeNum(n);
 			GenoData res = sub;
 			setGenoData(sub);
-			t0 = now_s();
-			double ll = resolveAll(sub, res);
-			double t = now_s() - t0;
-			printf(", \"resolve_n\": %d, \"resolve_s\": %.6f, \"resolve_steps\": %lld, \"resolve_ll\": %.17g", n, t, (long long) n * (genos.genotype_len() - head_len), ll);
+			printf(", \"resolve_n\": %d, \"resolve_offset\": %d, \"resolve_steps\": %lld, \"resolve_s\": [", n, off, (long long) n * (genos.genotype_len() - head_len));
+			double ll = 0;
+			for (int it = 0; it < opt.time_warmup + opt.time_steps; ++it) {
+				t0 = now_s();
+				ll = resolveAll(sub, res);
+				double t = now_s() - t0;
+				if (it >= opt.time_warmup) printf("%s%.6f", it > opt.time_warmup ? ", " : "", t);
+			}
+			printf("], \"resolve_ll\": %.17g", ll);
 			if (opt.time_estep > 0) {
 				int m = min(opt.time_estep, n);
 				sub.setGenotypeNum(m);
@@ -228,7 +236,7 @@ public:
 				for (int i = 0; i < pattern_num(); ++i) patterns.push_back(new HaploPattern(*m_patterns[i]));
 				t0 = now_s();
 				estimateFrequency(patterns);
-				t = now_s() - t0;
+				double t = now_s() - t0;
 				printf(", \"estep_n\": %d, \"estep_s\": %.6f, \"estep_steps\": %lld", m, t, (long long) m * (genos.genotype_len() - head_len));
 				DeleteAll_Clear()(patterns);
 			}
@@ -286,6 +294,9 @@ int main(int argc, char **argv)
 		else if (a == "--out-suffix") m.opt.out_suffix = next();
 		else if (a == "--time-resolve") m.opt.time_resolve = atoi(next());
 		else if (a == "--time-estep") m.opt.time_estep = atoi(next());
+		else if (a == "--time-offset") m.opt.time_offset = atoi(next());
+		else if (a == "--time-steps") m.opt.time_steps = atoi(next());
+		else if (a == "--time-warmup") m.opt.time_warmup = atoi(next());
 		else if (a[0] == '-') { usage(); return 2; }
 		else m.opt.input = a;
 	}

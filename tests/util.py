@@ -54,3 +54,24 @@ def rel_close(x, y, tol=1e-9):
     den = np.maximum(np.abs(x), np.abs(y))
     ok = (np.abs(x - y) <= tol * den) | (x == y)
     return bool(np.all(ok))
+
+
+def path_prior(m: dict, h0: np.ndarray, h1: np.ndarray) -> float:
+    """prior_probability of one phased pair under the automaton `m` (export_model layout): the product the reference builds along
+    the path -- head f_a*f_b (HaploPair.cpp:27), then *= tp_a*tp_b per locus (HaploPair.cpp:42,51) -- doubled unless the pair is
+    homozygous throughout (HaploBuilder.cpp:98).  Returns 0.0 when the path leaves the automaton."""
+    hl = int(m["head_len"])
+    heads = {}
+    for h in m["heads"]:
+        heads[bytes(m["al"][m["al_off"][h]:m["al_off"][h + 1]])] = int(h)
+    a = heads.get(bytes(h0[:hl].astype(np.int8)))
+    b = heads.get(bytes(h1[:hl].astype(np.int8)))
+    if a is None or b is None:
+        return 0.0
+    like = float(m["freq"][a]) * float(m["freq"][b])
+    for l in range(hl, len(h0)):
+        a = int(m["succ"][a, h0[l]]); b = int(m["succ"][b, h1[l]])
+        if a < 0 or b < 0:
+            return 0.0
+        like *= float(m["tp"][a]) * float(m["tp"][b])
+    return like if np.array_equal(h0, h1) else like * 2.0
