@@ -264,7 +264,7 @@ static int pick_threads(const hmc_ctx *ctx)
 {
     const char *env = getenv("HMC_B200_THREADS");
     int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
-    if (nt == 0) nt = ctx->missing_frac > 0.02 ? 256 : 128;
+    if (nt == 0) nt = 128;
     if (nt != 32 && nt != 33 && nt != 64 && nt != 128 && nt != 256) nt = 128;
     return nt;
 }
@@ -319,8 +319,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         const int n_wave = (int) std::min<size_t>(pending.size(), (size_t) wave_cap);
         ScratchPool &pl = big_mode ? ctx->big_pool : ctx->pool;
         int slots;
-        if (big_mode) { slots = std::min(n_wave, 4); rc = build_pool(ctx, pl, slots, K, 1 << 22, 1 << 24, 1 << 25); }
-        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, K, 1 << 15, 1 << 17, 1 << 18); }
+        if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, K, 1 << 20, 1 << 22, 1 << 23); }
+        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, K, 1 << 16, 1 << 18, 1 << 19); }
         if (rc) return rc;
         ctx->h_wave.assign(pending.begin(), pending.begin() + n_wave);
         CK(cudaMemcpyAsync(ctx->d_wave.p, ctx->h_wave.data(), sizeof(int) * n_wave, cudaMemcpyHostToDevice, ctx->stream));

@@ -26,7 +26,7 @@
 namespace hmc {
 
 #ifdef HMC_PROFILE_PASSES
-#define PASS_MARK(slot) do { const long long t_ = clock64(); if (tid == 0) pass_cyc[(slot) + pass_base] += t_ - t_mark; t_mark = t_; } while (0)
+#define PASS_MARK(slot) do { const long long t_ = clock64(); if (tid == 0) { if (pass_fast) pass_cyc[slot] += t_ - t_mark; else pass_cyc[(slot) + 8] += t_ - t_mark; } t_mark = t_; } while (0)
 #else
 #define PASS_MARK(slot) do { } while (0)
 #endif
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
         }
 #ifdef HMC_PROFILE_PASSES
         long long pass_cyc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int pass_base = 0;
+        bool pass_fast = true;
         long long t_mark = clock64();
 #endif
         par = 0;
@@ -253,11 +253,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
             int hsize = 64;
             while (hsize < 2 * C) hsize <<= 1;
             const bool fast = (C <= CC);
-            if (!fast && (C > sc.ccap || hsize > sc.hcap || C > sc.scap)) { status = ST_TOO_BIG; break; }
+            if (!fast && (C > sc.ccap || hsize > sc.hcap)) { status = ST_TOO_BIG; break; }
             if (!fast) ++c_spill;
 #ifdef HMC_PROFILE_PASSES
-            pass_base = fast ? 0 : 8;
-            if (tid == 0) pass_cyc[6 + pass_base] += C;
+            pass_fast = fast;
+            if (tid == 0) { if (fast) pass_cyc[6] += C; else pass_cyc[14] += C; }
 #endif
 
             int S_out = 0, new_exp = cur_exp;

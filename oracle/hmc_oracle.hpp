@@ -374,6 +374,7 @@ struct LinkGreater { bool operator()(const Link &a, const Link &b) const { retur
 struct State {
     int ida, idb;
     double tp, alpha, beta;
+    int nin = 0;                    // arrivals (addHaploPair calls) into this state -- statistics only
     std::vector<Link> links;        // m_best_links
     std::vector<int> fwd[2];        // m_forward_links[reversed]
 };
@@ -485,6 +486,7 @@ struct Builder {
                     k0 = t->links.size();
                     cur[s].fwd[reversed ? 1 : 0].push_back(it->second);
                 }
+                t->nin++;
                 t->links.insert(t->links.end(), pl.begin(), pl.end());
                 for (size_t k = k0; k < t->links.size(); ++k) {
                     t->links[k].link = (int) s;

@@ -146,7 +146,7 @@ void orc_trellis_get(void *p, int *ida, int *idb, double *alpha, double *tp, dou
     for (int l = 0; l <= h->hm.panel.L; ++l)
         for (const State &s : h->hm.builder.at[l]) {
             ida[k] = s.ida; idb[k] = s.idb; alpha[k] = s.alpha; tp[k] = s.tp; beta[k] = s.beta;
-            narr[k] = (int) (s.fwd[0].size() + s.fwd[1].size());
+            narr[k] = (int) (s.fwd[0].size() + s.fwd[1].size()) | (s.nin << 8);
             ++k;
         }
 }
