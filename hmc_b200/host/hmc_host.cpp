@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 
 namespace hmc_host {
 
@@ -674,12 +675,26 @@ void HaploBuilder::resolveAll(int sample_size, ResolveResult &r, bool want_haps)
 {
     uploadModel();
     const int N = m_genos->N, L = m_genos->L, K = sample_size > 1 ? sample_size : 1;
+    const int first = m_shard_count >= 0 ? m_shard_first : 0, count = m_shard_count >= 0 ? m_shard_count : N;
     r.K = K;
     r.pg.assign(N, 0); r.coverage.assign(N, 0); r.exp2.assign(N, 0); r.nres.assign(N, 0);
     r.prior.assign((size_t) N * K, 0); r.posterior.assign((size_t) N * K, 0);
     if (want_haps) r.haps.assign((size_t) N * K * 2 * L, -1); else r.haps.clear();
-    ck(m_ctx, hmc_resolve_all(m_ctx, 0, N, K, m_flags, r.pg.data(), r.exp2.data(), r.coverage.data(), r.nres.data(), r.prior.data(), r.posterior.data(),
-                              want_haps ? r.haps.data() : nullptr, &r.ll), "hmc_resolve_all");
+    double ll_shard = 0;
+    if (count > 0)
+        ck(m_ctx, hmc_resolve_all(m_ctx, first, count, K, m_flags, r.pg.data() + first, r.exp2.data() + first, r.coverage.data() + first, r.nres.data() + first,
+                                  r.prior.data() + (size_t) first * K, r.posterior.data() + (size_t) first * K,
+                                  want_haps ? r.haps.data() + (size_t) first * K * 2 * L : nullptr, &ll_shard), "hmc_resolve_all");
+    if (count < N && gather) {      // every rank ends up with every individual's result, in individual order
+        auto all = [&](auto &v, size_t per) { std::vector<typename std::remove_reference<decltype(v)>::type::value_type> full(v.size());
+                                              gather(v.data() + (size_t) first * per, full.data(), per * sizeof(v[0])); v.swap(full); };
+        all(r.pg, 1); all(r.exp2, 1); all(r.coverage, 1); all(r.nres, 1); all(r.prior, K); all(r.posterior, K);
+        if (want_haps) all(r.haps, (size_t) K * 2 * L);
+    }
+    // HaploModel.cpp:110: sum of log P(G) in individual order (identical on every rank and for every shard count)
+    r.ll = 0;
+    for (int i = 0; i < N; ++i) r.ll += r.exp2[i] ? (std::log(r.pg[i]) - r.exp2[i] * M_LN2) : std::log(r.pg[i]);
+    if (count == N) r.ll = ll_shard;
 }
 
 void HaploBuilder::estimateFrequency(PatternSet &patterns)
@@ -696,10 +711,14 @@ void HaploBuilder::estimateFrequency(PatternSet &patterns)
         al.insert(al.end(), patterns.al(p), patterns.al(p) + p.length());
     }
     off[Pc] = (int64_t) al.size();
-    std::vector<double> f(Pc), pf(Pc), tp(Pc);
-    ck(m_ctx, hmc_estimate_counts(m_ctx, 0, N, m_flags, Pc, start.data(), off.data(), al.data(), m_genos->genotype_probability.data(),
-                                  (m_flags & HMC_FLAG_SCALED) ? pg_exp.data() : nullptr, f.data(), pf.data()), "hmc_estimate_counts");
-    hmc_normalise_counts(Pc, N, f.data(), pf.data(), tp.data());
+    const int first = m_shard_count >= 0 ? m_shard_first : 0, count = m_shard_count >= 0 ? m_shard_count : N;
+    std::vector<double> raw((size_t) 2 * Pc, 0.0), tp(Pc);
+    double *f = raw.data(), *pf = raw.data() + Pc;
+    if (count > 0)
+        ck(m_ctx, hmc_estimate_counts(m_ctx, first, count, m_flags, Pc, start.data(), off.data(), al.data(), m_genos->genotype_probability.data() + first,
+                                      (m_flags & HMC_FLAG_SCALED) ? pg_exp.data() + first : nullptr, f, pf), "hmc_estimate_counts");
+    if (count < N && reduce_counts) reduce_counts(raw.data(), raw.size());     // the one exchange of an exact E-pass
+    hmc_normalise_counts(Pc, N, f, pf, tp.data());
     for (int i = 0; i < Pc; ++i) { patterns.pats[i].frequency = f[i]; patterns.pats[i].prefix_freq = pf[i]; patterns.pats[i].setTransitionProb(tp[i]); }
 }
 

@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -128,6 +129,7 @@ protected:
     size_t m_arena_bytes = 0;
     bool m_model_dirty = true, m_panel_dirty = true;
     unsigned m_flags = 0;
+    int m_shard_first = 0, m_shard_count = -1;     // this rank's block of individuals (-1 = all)
 
 public:
     explicit HaploBuilder(int device = 0, size_t arena_bytes = 0, int threads = 0);
@@ -146,6 +148,13 @@ public:
     void setScaled(bool on) { m_flags = on ? (m_flags | HMC_FLAG_SCALED) : (m_flags & ~HMC_FLAG_SCALED); }
     unsigned flags() const { return m_flags; }
     void markModelDirty() { m_model_dirty = true; }
+
+    // Multi-GPU (one process per GPU): individuals [first, first+count) are this rank's; the collectives are supplied by the
+    // launcher (torch.distributed / NCCL / MPI).  reduce_counts: in-place sum over ranks of n doubles.  gather: every rank
+    // contributes its individuals' records (elem_bytes each, contiguous) and receives all N records in individual order.
+    void setShard(int first, int count) { m_shard_first = first; m_shard_count = count; }
+    std::function<void(double *, size_t)> reduce_counts;
+    std::function<void(const void *, void *, size_t)> gather;
 
     void setGenoData(GenoData &genos);          // HaploBuilder.cpp:19-23
     void uploadPanel();                         // hmc_set_panel when the panel changed

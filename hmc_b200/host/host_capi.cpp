@@ -113,6 +113,15 @@ void hmch_get_trace(void *p, double *ll, int *npat)
     for (size_t i = 0; i < h->hm->ll_trace.size(); ++i) { ll[i] = h->hm->ll_trace[i]; npat[i] = h->hm->npat_trace[i]; }
 }
 void hmch_get_seconds(void *p, double *out3) { Handle *h = (Handle *) p; for (int i = 0; i < 3; ++i) out3[i] = h->hm->seconds[i]; }
+int hmch_set_shard(void *p, int first, int count) { Handle *h = (Handle *) p; GUARD(h->hm->setShard(first, count)); }
+typedef void (*hmch_reduce_fn)(double *buf, size_t n);
+typedef void (*hmch_gather_fn)(const void *send, void *recv_all, size_t elem_bytes);
+int hmch_set_collectives(void *p, hmch_reduce_fn reduce, hmch_gather_fn gather)
+{
+    Handle *h = (Handle *) p;
+    GUARD(if (reduce) h->hm->reduce_counts = [reduce](double *b, size_t n) { reduce(b, n); }; else h->hm->reduce_counts = nullptr;
+          if (gather) h->hm->gather = [gather](const void *s, void *r, size_t e) { gather(s, r, e); }; else h->hm->gather = nullptr);
+}
 int hmch_write_reconstructed(void *p, const char *path, const char *suffix)
 {
     Handle *h = (Handle *) p;
