@@ -132,6 +132,17 @@ __global__ void pack_kernel(const signed char *geno, int N, int L, int bits, int
     packed[t] = v;
 }
 
+// K0: successor table flattening, one thread per (pattern, allele)
+__global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P, int4 *out, int *)
+{
+    const size_t q = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int id = succ[q];
+    if (id >= P) id = -1;
+    const double t = id >= 0 ? tp[id] : 0.0;
+    out[q] = make_int4(id, 0, __double2loint(t), __double2hiint(t));
+}
+
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CC, int CL, int KMAX>
 static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
@@ -514,18 +525,8 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
         for (int j = 0; j < head_len; ++j) code += (long long) alleles[al_off[id] + j] * stride[j];
         lut[(size_t) code] = id;
     }
-    // 16-byte successor entries: one 128-bit gather yields the successor and its transition probability
-    std::vector<int4> s16((size_t) P * A);
-    for (size_t q = 0; q < (size_t) P * A; ++q) {
-        const int id = succ[q];
-        if (id >= P) return ctx->fail(HMC_ERR_INVALID, "successor id out of range");
-        const double t = id >= 0 ? tp[id] : 0.0;
-        long long bits;
-        memcpy(&bits, &t, 8);
-        s16[q] = make_int4(id, 0, (int) (bits & 0xFFFFFFFFll), (int) (bits >> 32));
-    }
+    for (size_t q = 0; q < (size_t) P * A; ++q) if (succ[q] >= P || succ[q] < -1) return ctx->fail(HMC_ERR_INVALID, "successor id out of range");
     CK(ctx->d_succ16.ensure((size_t) P * A));
-    CK(cudaMemcpyAsync(ctx->d_succ16.p, s16.data(), sizeof(int4) * (size_t) P * A, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_succ.ensure((size_t) P * A)); CK(ctx->d_start.ensure(P)); CK(ctx->d_tp.ensure(P)); CK(ctx->d_freq.ensure(P)); CK(ctx->d_last.ensure(P));
     CK(ctx->d_al_off.ensure(P + 1)); CK(ctx->d_al.ensure((size_t) al_off[P] + 1)); CK(ctx->d_heads.ensure(std::max(1, n_heads))); CK(ctx->d_head_lut.ensure(lut.size()));
     cudaStream_t st = ctx->stream;
@@ -538,6 +539,12 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     CK(cudaMemcpyAsync(ctx->d_al.p, alleles, (size_t) al_off[P], cudaMemcpyHostToDevice, st));
     if (n_heads > 0) CK(cudaMemcpyAsync(ctx->d_heads.p, heads, sizeof(int) * n_heads, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_head_lut.p, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice, st));
+    // 16-byte successor entries {successor id, pad, transition_prob(successor)}: one 128-bit gather yields both (K0 flatten)
+    {
+        const size_t n = (size_t) P * A;
+        succ16_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(ctx->d_succ.p, ctx->d_tp.p, n, P, ctx->d_succ16.p, ctx->d_flags.p ? ctx->d_flags.p + 1 : nullptr);
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(st));
     DevModel &m = ctx->dm;
     m.P = P; m.head_len = head_len; m.n_heads = n_heads; m.Amax = A;
