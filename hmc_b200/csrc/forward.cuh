@@ -83,7 +83,8 @@ struct FwdSmem {
     long long ll[4];                // -, alloc result, chunk cursor, chunk end
     long long tmp[8];               // scan scratch
     u32 ord[HC], cnt[HC];
-    int cand[CC], arr[CC], aoff[CC + 1], slot_of[CC];
+    alignas(16) int cand[CC];
+    int arr[CC], aoff[CC + 1], slot_of[CC];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
     int ints[4];
@@ -361,24 +362,45 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 PASS_MARK(1);
 
                 // ---- pass B+C: creators in ordinal order -> new state indices and arrival-segment offsets ----
+                // each lane owns UB consecutive ordinals, so the loads of a lane are independent and one block scan serves UB*NT slots
                 int n_arr = 0;
-                for (int base = 0; base < C; base += NT) {
-                    const int c = base + tid;
-                    int creator = 0, h = 0, n = 0;
-                    if (c < C) {
-                        const int enc = cand[c];
-                        if (enc >= 0) { h = enc & 0x3FFFFFFF; creator = (ord[h] == (u32) c); if (creator) n = (int) cnt[h]; }
+                constexpr int UB = 4;
+                for (int base = 0; base < C; base += NT * UB) {
+                    const int c0 = base + tid * UB;
+                    int enc[UB], nn[UB];
+                    bool cr[UB];
+                    u32 ov[UB];
+                    if (c0 + UB <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
+                    else {
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
                     }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & 0x3FFFFFFF] : 0xFFFFFFFFu;
+                    int ncr = 0, nar = 0;
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
+                        nn[u] = cr[u] ? (int) cnt[enc[u] & 0x3FFFFFFF] : 0;
+                        ncr += cr[u] ? 1 : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) nar += nn[u];
                     // one scan for both: creators in the high half, arrivals in the low half
                     long long tot;
-                    const long long ex = BlockScan<NT>::run(((long long) creator << 32) | (long long) n, tot, sm.tmp);
-                    if (creator) {
-                        const int idx = S_out + (int) (ex >> 32);
-                        if (idx < sc.scap) {
-                            ord[h] = 0x80000000u | (u32) idx;     // never equals a later ordinal
-                            slot_of[idx] = h;
-                            aoff[idx] = n_arr + (int) (ex & 0xFFFFFFFFll);
-                            cnt[h] = 0;
+                    const long long ex = BlockScan<NT>::run(((long long) ncr << 32) | (long long) nar, tot, sm.tmp);
+                    int idx = S_out + (int) (ex >> 32), off = n_arr + (int) (ex & 0xFFFFFFFFll);
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        if (cr[u]) {
+                            const int h = enc[u] & 0x3FFFFFFF;
+                            if (idx < sc.scap) {
+                                ord[h] = 0x80000000u | (u32) idx;     // never equals a later ordinal
+                                slot_of[idx] = h;
+                                aoff[idx] = off;
+                                cnt[h] = 0;
+                            }
+                            ++idx; off += nn[u];
                         }
                     }
                     S_out += (int) (tot >> 32);
@@ -394,15 +416,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 PASS_MARK(2);
 
                 // ---- pass D: scatter arrivals (unordered inside a segment; sorted in E) ----
-                for (int c = tid; c < C; c += NT) {
-                    const int enc = cand[c];
-                    if (enc >= 0) {
-                        const int h = enc & 0x3FFFFFFF;
-                        const u32 rev = ((u32) enc >> 30) & 1u;
-                        const int idx = (int) (ord[h] & 0x7FFFFFFFu);
-                        const int pos = (int) atomicAdd(cnt + h, 1u);
-                        arr[aoff[idx] + pos] = (int) ((u32) c | (rev << 31));
-                        if (p.estep) fwd[c] = (int) ((u32) idx | (rev << 31));
+                for (int base = 0; base < C; base += NT * UB) {
+                    const int c0 = base + tid * UB;
+                    int enc[UB], idxv[UB], pos[UB];
+                    if (c0 + UB <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
+                    else {
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        idxv[u] = 0; pos[u] = 0;
+                        if (enc[u] >= 0) { const int h = enc[u] & 0x3FFFFFFF; idxv[u] = (int) (ord[h] & 0x7FFFFFFFu); pos[u] = (int) atomicAdd(cnt + h, 1u); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        if (enc[u] >= 0) {
+                            const u32 rev = ((u32) enc[u] >> 30) & 1u;
+                            arr[aoff[idxv[u]] + pos[u]] = (int) ((u32) (c0 + u) | (rev << 31));
+                            if (p.estep) fwd[c0 + u] = (int) ((u32) idxv[u] | (rev << 31));
+                        }
                     }
                 }
                 block_sync<NT>();
@@ -426,27 +459,46 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                     const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
                     const double tpv = tpvs[h];
                     const int a0 = aoff[idx], n = aoff[idx + 1] - a0;
-                    for (int j = 1; j < n; ++j) {           // ordinal order inside the segment
-                        const int e = arr[a0 + j];
-                        int q = j - 1;
-                        while (q >= 0 && (arr[a0 + q] & 0x7FFFFFFF) > (e & 0x7FFFFFFF)) { arr[a0 + q + 1] = arr[a0 + q]; --q; }
-                        arr[a0 + q + 1] = e;
+                    // ordinal order inside the segment: up to 8 arrivals are sorted in registers (one batch of loads, a
+                    // 19-comparator network, one batch of stores); longer segments (< 1 % of arrivals) by insertion in place
+                    if (n > 1 && n <= 8) {
+                        int v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = (q < n) ? arr[a0 + q] : 0x7FFFFFFF;
+                        auto cx = [&](int a, int b) { const int x = v[a], y = v[b]; const bool sw = (x & 0x7FFFFFFF) > (y & 0x7FFFFFFF); v[a] = sw ? y : x; v[b] = sw ? x : y; };
+                        cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
+                        cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
+                        cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
+                        cx(1, 5); cx(2, 6);
+                        cx(1, 4); cx(3, 6);
+                        cx(2, 4); cx(3, 5);
+                        cx(3, 4);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (q < n) arr[a0 + q] = v[q];
+                    }
+                    else {
+                        for (int j = 1; j < n; ++j) {
+                            const int e = arr[a0 + j];
+                            int q = j - 1;
+                            while (q >= 0 && (arr[a0 + q] & 0x7FFFFFFF) > (e & 0x7FFFFFFF)) { arr[a0 + q + 1] = arr[a0 + q]; --q; }
+                            arr[a0 + q + 1] = e;
+                        }
                     }
                     double alpha = 0.0;
                     double bl[KMAX];
                     u32 bb[KMAX];
                     int nl_out = 0, xa = 0, ya = 0;
+                    // software pipeline over the arrivals: the predecessor's alpha and list header of arrival j+1 are requested
+                    // before arrival j is merged (the list itself is read in one batch of independent loads)
+                    int nx_e = arr[a0], nx_g, nx_s, nx_dir;
+                    decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
+                    u64 nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
+                    double nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
                     for (int j = 0; j < n; ++j) {
-                        const int e = arr[a0 + j];
-                        const u32 rev = (u32) e >> 31;
-                        int g, s, dir;
-                        decode(e & 0x7FFFFFFF, g, s, dir);
-                        const bool het = (sm.gx[g] != sm.gy[g]);
-                        if (j == 0) { const int x = dir ? sm.gy[g] : sm.gx[g], y = dir ? sm.gx[g] : sm.gy[g]; xa = rev ? y : x; ya = rev ? x : y; }
-                        // the predecessor's whole list in one batch of independent loads (sorted descending)
-                        const u64 mt = lk_in_cache ? sm.meta[par][s] : meta_in[s];
+                        const int e = nx_e, g = nx_g, s = nx_s, dir = nx_dir;
+                        const u64 mt = nx_mt;
+                        const double ain = nx_ain;
                         const int nl = (int) (mt & 0xFF);
-                        u32 hom = (u32) (mt >> 8);
                         double x[KMAX];
                         if (lk_in_cache) {
 #pragma unroll
@@ -457,7 +509,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
 #pragma unroll
                             for (int k = 0; k < KMAX; ++k) x[k] = (k < nl) ? lp[k] : 0.0;
                         }
-                        const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
+                        if (j + 1 < n) {
+                            nx_e = arr[a0 + j + 1];
+                            decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
+                            nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
+                            nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
+                        }
+                        const u32 rev = (u32) e >> 31;
+                        const bool het = (sm.gx[g] != sm.gy[g]);
+                        if (j == 0) { const int xx = dir ? sm.gy[g] : sm.gx[g], yy = dir ? sm.gx[g] : sm.gy[g]; xa = rev ? yy : xx; ya = rev ? xx : yy; }
+                        u32 hom = (u32) (mt >> 8);
                         const double term = __dmul_rn(ain, tpv);
                         alpha = (j == 0) ? term : __dadd_rn(alpha, term);
                         nl_out += nl;
