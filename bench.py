@@ -84,12 +84,15 @@ def algorithmic_bytes(c: dict, K: int) -> float:
     return 24.0 * c["arrivals"] + c["states"] * (24 + 16 * K) + c["states"] * (16 + 8 * K)
 
 
-def make_workload(n_gpus: int):
+def make_workload(shard: int = 0):
+    """The C2 panel (shard 0) or, for rank r > 0, another n_ind individuals drawn from the same founder population.
+    Weak scaling keeps the per-GPU work fixed: every rank resolves its own 2,000 individuals against the SAME model, the one mined
+    from the C2 panel (a model mined from a panel that grows with the GPU count would also grow the work per individual)."""
     from hmc_b200.synth import CONFIGS, make_panel
     N, L, A, F, m, seed, kind = CONFIGS[WORKLOAD]
     n_ind = env_int("HMC_BENCH_N", N)
     n_loci = env_int("HMC_BENCH_L", L)
-    g = make_panel(n_ind * n_gpus, n_loci, alleles=A, founders=F, missing=m, seed=seed)
+    g = make_panel(n_ind, n_loci, alleles=A, founders=F, missing=m, seed=seed, shard=shard)
     return g, kind, n_ind, n_loci
 
 
@@ -110,16 +113,20 @@ def run_ours(args):
 
     from hmc_b200 import HaploModel
 
-    g, kind, n_ind, n_loci = make_workload(n_gpus)
+    g, kind, n_ind, n_loci = make_workload(0)
     t0 = time.time()
     hm = HaploModel(device=local, host_threads=max(1, (os.cpu_count() or 8) // n_gpus))
-    hm.set_panel(g, kind)               # the whole panel: the M-step (mining) is replicated on every rank
+    hm.set_panel(g, kind)               # the C2 panel: the M-step (mining) is replicated on every rank
     hm.build()
     model = hm.export_model()
     t_model = time.time() - t0
     idx, n_alleles, allele_freq = hm.panel()
-    first = rank * n_ind                # this rank's shard of individuals (no data-path collective)
-    shard = np.ascontiguousarray(idx[first:first + n_ind])
+    if rank == 0:
+        shard = np.ascontiguousarray(idx)
+    else:                               # this rank's own individuals (no data-path collective); biallelic codes are the allele indices
+        gs, _, _, _ = make_workload(rank)
+        assert int(n_alleles.min()) == 2, "shard genotypes assume both alleles occur at every locus of the C2 panel"
+        shard = np.ascontiguousarray(gs.astype(np.int8))
 
     # pinned host staging for the end-to-end leg
     def pinned(a):
@@ -231,7 +238,7 @@ def run_ours(args):
                    "pass": "HaploModel::resolveAll = K1 forward + K2 traceback", "patterns": int(model["P"]), "steps_per_pass": int(total_steps),
                    "mean_states": counters["states"] / max(counters["steps"], 1), "arrivals_per_step": counters["arrivals"] / max(counters["steps"], 1),
                    "max_states": counters["max_states"], "l2": "trellis + model working set (GBs) exceeds the 126 MB L2; no flush needed",
-                   "model_build_s": t_model, "sharding": "individuals; model replicated; LL all-reduce only"},
+                   "model_build_s": t_model, "sharding": "each rank resolves its own 2,000 individuals (rank r > 0: fresh draws from the same founders) against the replicated C2 model; LL all-reduce only"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
         "kernel_ms": {"forward": float(np.mean(fwd_ms)), "traceback": float(np.mean(tb_ms)), "device_total": dev_ms},
@@ -277,7 +284,7 @@ def run_reference(args):
         return
     n_gpus = max(env_int("WORLD_SIZE", 1), 1)
     from hmc_b200.synth import write_phase
-    g, kind, n_ind, n_loci = make_workload(1)
+    g, kind, n_ind, n_loci = make_workload(0)
     ref = os.path.join(ROOT, "oracle", "_ref", "hmc_ref")
     if not os.path.exists(ref):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/hmc_ref was not built (needs /root/reference at build time)"}))

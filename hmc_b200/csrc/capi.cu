@@ -60,6 +60,7 @@ struct hmc_ctx {
     int N = 0, L = 0, Amax = 0, bits = 0, words = 0;
     double missing_frac = 0;
     DevBuf<u32> d_packed, d_linfo;
+    DevBuf<signed char> d_raw;      // staging of the unpacked genotypes (kept: cudaMalloc/cudaFree per call cost 100s of ms)
     DevBuf<int> d_order;
     std::vector<int> h_order, h_rank;
     std::vector<int> h_nall;
@@ -226,7 +227,7 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
     const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_s = al((size_t) (scap + 1) * 4);
     const size_t b_like = al((size_t) scap * K * 8), b_meta = al((size_t) scap * 8);
     const size_t b_obp = al((size_t) scap * K * 4);
-    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 2 * b_s + 2 * b_like + 3 * b_meta + b_obp;
+    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 3 * b_s + 2 * b_like + 3 * b_meta + b_obp;
     CK(pl.mem.ensure(per * slots));
     CK(pl.desc.ensure(slots));
     std::vector<Scratch> h(slots);
@@ -243,6 +244,7 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
         s.arr = (int *) b; b += b_c;
         s.aoff = (int *) b; b += b_s;
         s.slot_of = (int *) b; b += b_s;
+        s.order = (int *) b; b += b_s;
         s.like[0] = (double *) b; b += b_like;
         s.like[1] = (double *) b; b += b_like;
         s.meta[0] = (u64 *) b; b += b_meta;
@@ -436,7 +438,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_packed.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
+    ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
     ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
@@ -486,7 +488,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     CK(ctx->d_packed.ensure((size_t) N * ctx->words));
     CK(ctx->d_linfo.ensure(L));
     CK(ctx->d_order.ensure(N));
-    DevBuf<signed char> raw;
+    DevBuf<signed char> &raw = ctx->d_raw;
     CK(raw.ensure((size_t) N * 2 * L));
     CK(cudaMemcpyAsync(raw.p, geno, (size_t) N * 2 * L, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_linfo.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, ctx->stream));
@@ -495,7 +497,6 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     pack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, ctx->stream>>>(raw.p, N, L, ctx->bits, ctx->words, ctx->d_packed.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    raw.release();
     return HMC_OK;
 }
 

@@ -78,6 +78,7 @@ struct Scratch {
     u32 *ord, *cnt, *nidx;      // [hcap]
     int *cand, *arr;            // [ccap]
     int *aoff, *slot_of;        // [scap+1], [scap]
+    int *order;                 // [scap] pass-E visiting order (light states first)
     double *like[2];            // [scap*K]
     u64 *meta[2];               // [scap]  (links | hom mask << 8)
 };

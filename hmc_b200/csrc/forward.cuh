@@ -84,7 +84,7 @@ struct FwdSmem {
     long long tmp[8];               // scan scratch
     u32 ord[HC], cnt[HC];
     alignas(16) int cand[CC];
-    int arr[CC], aoff[CC + 1], slot_of[CC];
+    int arr[CC], aoff[CC + 1], slot_of[CC], order[CC];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
     int ints[4];
@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 int *const arr = FAST ? sm.arr : sc.arr;
                 int *const aoff = FAST ? sm.aoff : sc.aoff;
                 int *const slot_of = FAST ? sm.slot_of : sc.slot_of;
+                int *const order = FAST ? sm.order : sc.order;
                 const u32 hmask = (u32) hsize - 1u;
                 for (int h = tid; h < hsize; h += NT) { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
 
@@ -363,8 +364,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
 
                 // ---- pass B+C: creators in ordinal order -> new state indices and arrival-segment offsets ----
                 // each lane owns UB consecutive ordinals, so the loads of a lane are independent and one block scan serves UB*NT slots
-                int n_arr = 0;
-                constexpr int UB = 4;
+                int n_arr = 0, n_heavy = 0;
+                constexpr int UB = 4, HEAVY_N = 3;
+                const int ocap = FAST ? CC : sc.scap;
                 for (int base = 0; base < C; base += NT * UB) {
                     const int c0 = base + tid * UB;
                     int enc[UB], nn[UB];
@@ -377,19 +379,21 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & 0x3FFFFFFF] : 0xFFFFFFFFu;
-                    int ncr = 0, nar = 0;
+                    int ncr = 0, nar = 0, nhv = 0;
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
                         nn[u] = cr[u] ? (int) cnt[enc[u] & 0x3FFFFFFF] : 0;
                         ncr += cr[u] ? 1 : 0;
+                        nhv += nn[u] >= HEAVY_N ? 1 : 0;
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) nar += nn[u];
-                    // one scan for both: creators in the high half, arrivals in the low half
+                    // one scan for all three: heavy creators | creators | arrivals
                     long long tot;
-                    const long long ex = BlockScan<NT>::run(((long long) ncr << 32) | (long long) nar, tot, sm.tmp);
-                    int idx = S_out + (int) (ex >> 32), off = n_arr + (int) (ex & 0xFFFFFFFFll);
+                    const long long ex = BlockScan<NT>::run(((long long) nhv << 52) | ((long long) ncr << 40) | (long long) nar, tot, sm.tmp);
+                    int idx = S_out + (int) ((ex >> 40) & 0xFFF), off = n_arr + (int) (ex & 0xFFFFFFFFFFll);
+                    int hv = n_heavy + (int) (ex >> 52);
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         if (cr[u]) {
@@ -399,12 +403,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                                 slot_of[idx] = h;
                                 aoff[idx] = off;
                                 cnt[h] = 0;
+                                // pass E visits light states first and heavy ones (many arrivals) last, so that the lanes of a warp
+                                // iteration do similar amounts of work: light fill the front of `order`, heavy the back
+                                if (nn[u] >= HEAVY_N) { if (ocap - 1 - hv >= 0) order[ocap - 1 - hv] = idx; ++hv; }
+                                else order[idx - hv] = idx;
                             }
                             ++idx; off += nn[u];
                         }
                     }
-                    S_out += (int) (tot >> 32);
-                    n_arr += (int) (tot & 0xFFFFFFFFll);
+                    S_out += (int) ((tot >> 40) & 0xFFF);
+                    n_arr += (int) (tot & 0xFFFFFFFFFFll);
+                    n_heavy += (int) (tot >> 52);
                 }
                 if (S_out == 0) return 1;       // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82
                 if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; return 2; }
@@ -453,7 +462,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 const bool out_cache = S_out <= CC;
                 const bool lk_out_cache = S_out <= CL;
                 double amax = 0.0;
-                for (int idx = tid; idx < S_out; idx += NT) {
+                const int n_light = S_out - n_heavy;
+                for (int q = tid; q < S_out; q += NT) {
+                    const int idx = q < n_light ? order[q] : order[ocap - 1 - (q - n_light)];
                     const int h = slot_of[idx];
                     const u64 key = keys[h];
                     const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);

@@ -12,10 +12,13 @@ import numpy as np
 
 
 def make_panel(n_ind: int, n_loci: int, *, alleles: int = 2, founders: int = 8, missing: float = 0.0,
-               switch: float = 0.02, mutation: float = 0.005, seed: int = 1) -> np.ndarray:
-    """Return int8 array [n_ind, 2, n_loci] of allele codes 0..alleles-1, -1 = missing."""
+               switch: float = 0.02, mutation: float = 0.005, seed: int = 1, shard: int = 0) -> np.ndarray:
+    """Return int8 array [n_ind, 2, n_loci] of allele codes 0..alleles-1, -1 = missing.
+    shard > 0 draws a fresh set of individuals from the SAME founder population (multi-GPU weak-scaling shards)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     fnd = rng.integers(0, alleles, size=(founders, n_loci), dtype=np.int8)
+    if shard > 0:
+        rng = np.random.Generator(np.random.PCG64(seed * 1000003 + shard))
     h = n_ind * 2
     cur = rng.integers(0, founders, size=h)
     sw = rng.random((h, n_loci)) < switch
