@@ -145,10 +145,10 @@ __global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NT, int CC, int CL, int KMAX>
+template <int NT, int CC, int CL, int KMAX, int MINB = 512 / NT>
 static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
 {
-    auto kern = forward_kernel<NT, CC, CL, KMAX>;
+    auto kern = forward_kernel<NT, CC, CL, KMAX, MINB>;
     const size_t smem = sizeof(FwdSmem<NT, CC, CL, KMAX>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
@@ -197,8 +197,25 @@ static cudaError_t launch_forward(int nt, int kmax, const FwdParams &p, int grid
     switch (nt) {
         case 32: return launch_warp(kmax, p, grid, st, occ);
         case 33: return launch_forward_k<32, 128, 64>(kmax, p, grid, st, occ);
-        case 64: return launch_forward_k<64, 256, 96>(kmax, p, grid, st, occ);
-        case 128: return launch_forward_k<128, 512, 128>(kmax, p, grid, st, occ);
+        case 64:
+            switch (kmax) {
+                case 1: return launch_forward_t<64, 128, 64, 1, 8>(p, grid, st, occ);
+                case 4: return launch_forward_t<64, 128, 32, 4, 8>(p, grid, st, occ);
+                case 10: return launch_forward_t<64, 128, 16, 10, 8>(p, grid, st, occ);
+                case 16: return launch_forward_t<64, 128, 12, 16, 8>(p, grid, st, occ);
+                default: return launch_forward_t<64, 128, 8, 32, 8>(p, grid, st, occ);
+            }
+        case 128:
+            // Measured on C2 (profiles/README.md): small shared-memory footprints win -- what is not carved out as shared memory is L1
+            // for the successor gathers, the spilled hash / segment arrays and the K-best lists -- and 4-5 CTAs per SM beat larger
+            // fast-path capacities.
+            switch (kmax) {
+                case 1: return launch_forward_t<128, 256, 64, 1, 5>(p, grid, st, occ);
+                case 4: return launch_forward_t<128, 256, 64, 4, 4>(p, grid, st, occ);
+                case 10: return launch_forward_t<128, 256, 32, 10, 4>(p, grid, st, occ);
+                case 16: return launch_forward_t<128, 256, 24, 16, 4>(p, grid, st, occ);
+                default: return launch_forward_t<128, 256, 12, 32, 4>(p, grid, st, occ);
+            }
         default: return launch_forward_k<256, 1024, 256>(kmax, p, grid, st, occ);
     }
 }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void topk_insert(double (&bl)[KMAX], u32 (&bb)[KMAX],
 
 template <int NT, int CC, int CL, int KMAX>
 struct FwdSmem {
-    static constexpr int HC = 2 * CC;
+    static constexpr int HC = 2 * CC <= 256 ? 256 : 2 * CC <= 512 ? 512 : 2 * CC <= 1024 ? 1024 : 2 * CC <= 2048 ? 2048 : 4096;   // power of two >= 2 CC
     u64 keys[HC];
     double tpv[HC];
     double alpha[2][CC];
@@ -84,14 +84,14 @@ struct FwdSmem {
     long long tmp[8];               // scan scratch
     u32 ord[HC], cnt[HC];
     alignas(16) int cand[CC];
-    int arr[CC], aoff[CC + 1], slot_of[CC], order[CC];
+    int arr[CC], aoff[CC + 1], slot_of[CC];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
     int ints[4];
 };
 
-template <int NT, int CC, int CL, int KMAX>
-__global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
+template <int NT, int CC, int CL, int KMAX, int MINB>
+__global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 {
     typedef FwdSmem<NT, CC, CL, KMAX> Smem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 int *const arr = FAST ? sm.arr : sc.arr;
                 int *const aoff = FAST ? sm.aoff : sc.aoff;
                 int *const slot_of = FAST ? sm.slot_of : sc.slot_of;
-                int *const order = FAST ? sm.order : sc.order;
                 const u32 hmask = (u32) hsize - 1u;
                 for (int h = tid; h < hsize; h += NT) { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
 
@@ -403,10 +402,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                                 slot_of[idx] = h;
                                 aoff[idx] = off;
                                 cnt[h] = 0;
-                                // pass E visits light states first and heavy ones (many arrivals) last, so that the lanes of a warp
-                                // iteration do similar amounts of work: light fill the front of `order`, heavy the back
-                                if (nn[u] >= HEAVY_N) { if (ocap - 1 - hv >= 0) order[ocap - 1 - hv] = idx; ++hv; }
-                                else order[idx - hv] = idx;
                             }
                             ++idx; off += nn[u];
                         }
@@ -462,9 +457,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) forward_kernel(FwdParams p)
                 const bool out_cache = S_out <= CC;
                 const bool lk_out_cache = S_out <= CL;
                 double amax = 0.0;
-                const int n_light = S_out - n_heavy;
-                for (int q = tid; q < S_out; q += NT) {
-                    const int idx = q < n_light ? order[q] : order[ocap - 1 - (q - n_light)];
+                for (int idx = tid; idx < S_out; idx += NT) {
                     const int h = slot_of[idx];
                     const u64 key = keys[h];
                     const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
