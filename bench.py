@@ -176,7 +176,6 @@ def run_ours(args):
         launches += dev.counters()["launches"]
     barrier()
     elapsed = time.perf_counter() - t_begin
-    clocks = sampler.stop() if rank == 0 else None
     counters = dev.counters()
     steps_per_pass = counters["steps"]
     dev_ms = float(np.mean(fwd_ms) + np.mean(tb_ms))        # CUDA-event time of the kernels of one pass (timed on their stream)
@@ -194,6 +193,7 @@ def run_ours(args):
         res = dev.resolve_all(K=K_SAMPLE)
     barrier()
     e2e_elapsed = time.perf_counter() - t_begin
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     d2h = sum(res[k].nbytes for k in ("pg", "exp", "coverage", "nres", "prior", "posterior", "haps"))
 
     # max over ranks

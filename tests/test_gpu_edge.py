@@ -1,0 +1,120 @@
+"""-m gpu: edge cases of the C-ABI path (tiny / degenerate panels, limits, misuse), each against the oracle port."""
+import numpy as np
+import pytest
+
+from hmc_b200 import DeviceBuilder, HmcError, FLAG_SCALED
+from hmc_b200.synth import make_panel
+from oracle.pyoracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def both(g, K=10, threads=0, flags=0, **opts):
+    o = Oracle(g, sample_size=K, scaled=bool(flags & FLAG_SCALED), **opts)
+    o.find_patterns()
+    ll = o.resolve_all()
+    dev = DeviceBuilder(threads=threads)
+    nall, afreq = o.allele_table()
+    dev.set_panel(g, nall, afreq)
+    dev.set_model(o.export_model())
+    r = dev.resolve_all(K=K, flags=flags)
+    return o, ll, dev, r
+
+
+def check(o, ll, r, n):
+    assert (np.isneginf(ll) and np.isneginf(r["ll"])) or ll == r["ll"]
+    for i in range(n):
+        a = o.individual(i)
+        assert a["pg"] == r["pg"][i] and a["n"] == r["nres"][i]
+        assert np.array_equal(a["prior"], r["prior"][i, :a["n"]])
+
+
+@pytest.mark.parametrize("threads", [32, 128])
+def test_single_individual_two_loci(threads):
+    g = np.array([[[0, 1], [1, 0]]], np.int8)
+    o, ll, dev, r = both(g, threads=threads)
+    check(o, ll, r, 1)
+    dev.close()
+
+
+@pytest.mark.parametrize("threads", [32, 128])
+def test_one_locus_panel_has_no_steps(threads):
+    g = make_panel(12, 1, founders=2, seed=31)
+    g[0, 0, 0], g[0, 1, 0] = 0, 1       # make sure both alleles occur
+    o, ll, dev, r = both(g, threads=threads)
+    check(o, ll, r, 12)
+    assert dev.counters()["steps"] == 0
+    dev.close()
+
+
+@pytest.mark.parametrize("threads", [32, 128])
+def test_fully_missing_individual(threads):
+    g = make_panel(20, 16, founders=4, seed=32)
+    g[3] = -1                            # every genotype of individual 3 is missing: all allele pairs at every locus
+    g[7, :, :8] = -1
+    o, ll, dev, r = both(g, threads=threads, max_pattern_len=6)
+    check(o, ll, r, 20)
+    assert (r["haps"][3, 0] >= 0).all()
+    dev.close()
+
+
+def test_k_extremes():
+    g = make_panel(16, 30, founders=4, missing=0.05, seed=33)
+    for K in (1, 2, 16, 32):
+        o, ll, dev, r = both(g, K=K)
+        check(o, ll, r, 16)
+        dev.close()
+
+
+def test_sixteen_alleles_and_the_limit():
+    g = make_panel(40, 10, alleles=16, founders=24, seed=34)
+    o, ll, dev, r = both(g, max_pattern_len=4)
+    check(o, ll, r, 40)
+    dev.close()
+    dev = DeviceBuilder()
+    with pytest.raises(HmcError):
+        dev.set_panel(np.zeros((2, 2, 3), np.int8), np.full(3, 17, np.int32), np.zeros((3, 17)))
+    dev.close()
+
+
+def test_underflow_without_scaling_is_the_references_zero():
+    """L = 3000 unscaled: alpha underflows, every extension dies (HaploBuilder.cpp:237), P(G) = 0, no resolution -- like the reference."""
+    g = make_panel(6, 3000, founders=6, seed=35)
+    o, ll, dev, r = both(g, max_pattern_len=8)
+    assert np.isneginf(ll) and np.isneginf(r["ll"])
+    assert (r["nres"] == 0).all() and (r["pg"] == 0).all()
+    dev.close()
+    o, ll, dev, r = both(g, flags=FLAG_SCALED, max_pattern_len=8)
+    assert np.isfinite(ll) and ll == r["ll"] and (r["nres"] > 0).all()
+    dev.close()
+
+
+def test_misuse_is_an_error_code_not_a_crash():
+    dev = DeviceBuilder()
+    with pytest.raises(HmcError):
+        dev.resolve_all(K=1, count=1)               # no panel
+    g = make_panel(8, 10, founders=2, seed=36)
+    o = Oracle(g)
+    o.find_patterns()
+    nall, afreq = o.allele_table()
+    dev.set_panel(g, nall, afreq)
+    with pytest.raises(HmcError):
+        dev.resolve_all(K=1)                        # no model
+    m = o.export_model()
+    dev.set_model(m)
+    with pytest.raises(HmcError):
+        dev.resolve_all(K=33)                       # K limit
+    with pytest.raises(HmcError):
+        dev.resolve_all(K=1, first=4, count=8)      # range outside the panel
+    bad = dict(m)
+    bad["succ"] = m["succ"].copy()
+    bad["succ"][0, 0] = m["P"] + 5
+    with pytest.raises(HmcError):
+        dev.set_model(bad)
+    dev.set_model(m)
+    r = dev.resolve_all(K=3, first=2, count=4)      # a sub-range works and is indexed from `first`
+    o.set_options(sample_size=3)
+    o.resolve_all()
+    for i in range(4):
+        assert o.individual(2 + i)["pg"] == r["pg"][i]
+    dev.close()
