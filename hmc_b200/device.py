@@ -145,6 +145,22 @@ class DeviceBuilder:
         self._ck(lib().hmc_estimate_counts(self._h, first, count, flags, Pc, _p(start), _p(al_off), _p(al), _p(pg), _p(pe), _p(f), _p(pf)))
         return f, pf
 
+    def estimate_counts_device(self, start, al_off, al, pg, pg_exp=None, first: int = 0, count: int | None = None, flags: int = 0):
+        """E-pass whose raw sums stay in HBM: returns a zero-copy torch.float64 CUDA tensor of 2*Pc entries (frequency sums, then prefix
+        sums) owned by the context -- all-reduce it in place (NCCL) before fetching / normalising."""
+        import torch
+        count = self.N - first if count is None else count
+        start = np.ascontiguousarray(start, np.int32); al_off = np.ascontiguousarray(al_off, np.int64); al = np.ascontiguousarray(al, np.int8)
+        pg = np.ascontiguousarray(pg, np.float64)
+        pe = None if pg_exp is None else np.ascontiguousarray(pg_exp, np.int32)
+        Pc = len(start)
+        ptr = C.c_void_p()
+        self._ck(lib().hmc_estimate_counts_device(self._h, first, count, flags, Pc, _p(start), _p(al_off), _p(al), _p(pg), _p(pe), C.byref(ptr)))
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (2 * Pc,), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Buf(), device="cuda")
+
     @staticmethod
     def normalise_counts(freq, prefix, N):
         f = np.array(freq, np.float64); pf = np.array(prefix, np.float64); tp = np.zeros_like(f)
