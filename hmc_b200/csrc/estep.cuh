@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(128) backward_kernel(BackParams p)
 // ---------------------------------------------------------------------------------------------
 struct EstepScratch {       // per persistent warp
     double *acc;            // [3][smax] dense accumulators, zero between nodes
-    int *mark;              // [3][smax] first-touch flags, zero between nodes
     int *ekey;              // [ecap] entry stack: state * 4 + class
     double *ew;             // [ecap] entry weights
     int smax, ecap;
@@ -294,9 +293,10 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32) estep_kernel(EstepParams p)
                                 if (cls == 0) { if (aa == j && ab == j) nc = 0; else if (aa == j) { nc = 1; nw *= 0.5; } else if (ab == j) { nc = 2; nw *= 0.5; } }
                                 else if (cls == 1) { if (!rev) { if (aa == j) nc = 1; } else { if (ab == j) nc = 2; } }
                                 else { if (!rev) { if (ab == j) nc = 2; } else { if (aa == j) nc = 1; } }
-                                if (nc >= 0) {
-                                    atomicAdd(sc.acc + (size_t) nc * smax + t, nw);
-                                    if (atomicExch(sc.mark + (size_t) nc * smax + t, 1) == 0) {
+                                // weights are products of positive numbers: a zero one (underflow, tp = 0) changes no sum below it and is
+                                // dropped, so "the accumulator was 0" identifies the first contribution to (state, class) exactly
+                                if (nc >= 0 && nw > 0.0) {
+                                    if (atomicAdd(sc.acc + (size_t) nc * smax + t, nw) == 0.0) {
                                         const int pos = atomicAdd(&s_cnt[wi], 1);
                                         if (out0 + pos < sc.ecap) sc.ekey[out0 + pos] = t * 4 + nc;
                                     }
@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32) estep_kernel(EstepParams p)
                                 const double v = sc.acc[(size_t) nc * smax + t];
                                 sc.ew[out0 + q] = v;
                                 sc.acc[(size_t) nc * smax + t] = 0.0;
-                                sc.mark[(size_t) nc * smax + t] = 0;
                                 fsum += v * betan[t];
                             }
                         }

@@ -81,12 +81,14 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
         const int smax = (int) std::max<long long>(hc[2], 1);
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, estep_kernel, ESTEP_WARPS * 32, 0));
-        long long ecap = std::max<long long>(4096, 3LL * smax * 8);
+        long long ecap = std::max<long long>(4096, 3LL * smax * 2);     // entry stack; grown x4 and the wave retried if a task overflows it
         for (int attempt = 0; attempt < 4; ++attempt) {
             auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-            const size_t b_acc = al((size_t) 3 * smax * 8), b_mark = al((size_t) 3 * smax * 4), b_key = al((size_t) ecap * 4), b_w = al((size_t) ecap * 8);
-            const size_t per = b_acc + b_mark + b_key + b_w;
-            const size_t budget = (size_t) 12 << 30;
+            const size_t b_acc = al((size_t) 3 * smax * 8), b_key = al((size_t) ecap * 4), b_w = al((size_t) ecap * 8);
+            const size_t per = b_acc + b_key + b_w;
+            size_t fr = 0, tot = 0;
+            CK(cudaMemGetInfo(&fr, &tot));
+            const size_t budget = std::max<size_t>((size_t) 2 << 30, std::min<size_t>((size_t) 40 << 30, (fr + d_escr.n) / 2));
             long long warps = std::min<long long>((long long) ctx->sms * occ * ESTEP_WARPS, std::max<long long>(ESTEP_WARPS, (long long) (budget / per)));
             warps = std::min<long long>(warps, ((long long) n_wave * L + ESTEP_WARPS - 1));
             const int blocks = (int) std::max<long long>(1, warps / ESTEP_WARPS);
@@ -98,7 +100,6 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
             for (long long q = 0; q < warps; ++q) {
                 unsigned char *b = d_escr.p + per * q;
                 h[q].acc = (double *) b; b += b_acc;
-                h[q].mark = (int *) b; b += b_mark;
                 h[q].ekey = (int *) b; b += b_key;
                 h[q].ew = (double *) b;
                 h[q].smax = smax; h[q].ecap = (int) ecap;
