@@ -503,16 +503,9 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                         const u64 mt = nx_mt;
                         const double ain = nx_ain;
                         const int nl = (int) (mt & 0xFF);
-                        double x[KMAX];
-                        if (lk_in_cache) {
-#pragma unroll
-                            for (int k = 0; k < KMAX; ++k) x[k] = sm.like[par][s * KMAX + k];
-                        }
-                        else {
-                            const double *lp = like_in + (size_t) s * K;
-#pragma unroll
-                            for (int k = 0; k < KMAX; ++k) x[k] = (k < nl) ? lp[k] : 0.0;
-                        }
+                        // the predecessor's list (sorted descending) is read straight from where it lives: the first arrival copies it in one
+                        // batch of independent loads, later arrivals stream it with the next element always in flight
+                        const double *lp = lk_in_cache ? &sm.like[par][s * KMAX] : like_in + (size_t) s * K;
                         if (j + 1 < n) {
                             nx_e = arr[a0 + j + 1];
                             decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
@@ -535,7 +528,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             // scaling keeps the order: the first arrival's list is the initial top-K as it stands
 #pragma unroll
                             for (int k = 0; k < KMAX; ++k) {
-                                bl[k] = (k < nl) ? __dmul_rn(x[k], tpv) : -1.0;
+                                bl[k] = (k < nl) ? __dmul_rn(lp[k], tpv) : -1.0;
                                 bb[k] = bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u);
                             }
                         }
@@ -546,13 +539,14 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             }
                             // sorted input: stop at the first element that does not make the list (unless some were zeroed)
                             int k = 0;
+                            double cur = nl > 0 ? lp[0] : 0.0;
                             while (k < nl) {
-                                double lv = __dmul_rn(x[0], tpv);
+                                const double nxt = (k + 1 < nl) ? lp[k + 1] : 0.0;
+                                double lv = __dmul_rn(cur, tpv);
                                 if ((zero >> k) & 1u) lv = 0.0;
                                 if (lv > bl[KMAX - 1]) topk_insert<KMAX>(bl, bb, lv, bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u));
                                 else if (zero == 0) break;
-#pragma unroll
-                                for (int q = 0; q + 1 < KMAX; ++q) x[q] = x[q + 1];
+                                cur = nxt;
                                 ++k;
                             }
                         }
