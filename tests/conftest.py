@@ -9,7 +9,17 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
         sys.path.insert(0, p)
 
 
+def _ensure_built():
+    """The .so files are built artefacts (git-ignored); build them on first use so that a fresh checkout can run the suite."""
+    from hmc_b200 import build as b
+    if not os.path.exists(b.SO):
+        b.build()
+    if not os.path.exists(b.HOST_SO) or not os.path.exists(b.CLI):
+        b.build_host()
+
+
 def pytest_configure(config):
+    _ensure_built()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "ref: needs the reference sources at /root/reference (build container only)")
 
