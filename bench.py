@@ -250,7 +250,7 @@ def run_ours(args):
         except Exception:
             traffic = None
 
-    cpu = cpu_baseline(shard, n_alleles, allele_freq, model, n_loci)
+    cpu = cpu_baseline(shard, n_alleles, allele_freq, model, n_loci) if n_gpus == 1 else None      # reported at N = 1 only
 
     line = {
         "metric": "individual x locus phasing steps/sec per EM iteration", "value": value, "unit": "steps/s", "n_gpus": n_gpus,
