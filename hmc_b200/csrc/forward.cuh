@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             else add_group(g0, g1);
             if (tid == 0) sm.gbase[ng] = C;
             int hsize = 64;
-            while (hsize < 2 * C) hsize <<= 1;
+            while (hsize * 4 < 5 * C) hsize <<= 1;     // load factor <= 0.8 even if every candidate were a new state
             const bool fast = (C <= CC);
             if (!fast && (C > sc.ccap || hsize > sc.hcap)) { status = ST_TOO_BIG; break; }
             if (!fast) ++c_spill;
@@ -498,10 +498,12 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
                     u64 nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
                     double nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
+                    double nx_l0 = lk_in_cache ? sm.like[par][nx_s * KMAX] : like_in[(size_t) nx_s * K];    // every list has >= 1 link
                     for (int j = 0; j < n; ++j) {
                         const int e = nx_e, g = nx_g, s = nx_s, dir = nx_dir;
                         const u64 mt = nx_mt;
                         const double ain = nx_ain;
+                        const double l0 = nx_l0;
                         const int nl = (int) (mt & 0xFF);
                         // the predecessor's list (sorted descending) is read straight from where it lives: the first arrival copies it in one
                         // batch of independent loads, later arrivals stream it with the next element always in flight
@@ -511,6 +513,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
                             nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
                             nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
+                            nx_l0 = lk_in_cache ? sm.like[par][nx_s * KMAX] : like_in[(size_t) nx_s * K];
                         }
                         const u32 rev = (u32) e >> 31;
                         const bool het = (sm.gx[g] != sm.gy[g]);
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             }
                             // sorted input: stop at the first element that does not make the list (unless some were zeroed)
                             int k = 0;
-                            double cur = nl > 0 ? lp[0] : 0.0;
+                            double cur = l0;
                             while (k < nl) {
                                 const double nxt = (k + 1 < nl) ? lp[k + 1] : 0.0;
                                 double lv = __dmul_rn(cur, tpv);
