@@ -48,6 +48,12 @@ struct ScratchPool {
     DevBuf<Scratch> desc;
 };
 
+struct EstepTrie {      // host-built flattened ForwardPatternTree + its device copy
+    DevBuf<int> d_root, d_child, d_data;
+    DevTrie dev = {};
+    void release() { d_root.release(); d_child.release(); d_data.release(); }
+};
+
 struct hmc_ctx {
     int device = 0;
     int sms = 0;
@@ -96,6 +102,10 @@ struct hmc_ctx {
 
     // E-step
     DevBuf<double> d_counts, d_pgin;
+    EstepTrie trie;
+    DevBuf<int> d_bexp, d_eflags;
+    DevBuf<unsigned char> d_escr;
+    DevBuf<EstepScratch> d_edesc;
     DevBuf<int> d_pgexp;
 
     int64_t counters[HMC_CNT_N] = {};
@@ -463,6 +473,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
     ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
+    ctx->trie.release(); ctx->d_bexp.release(); ctx->d_eflags.release(); ctx->d_escr.release(); ctx->d_edesc.release(); ctx->d_cycles.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -1,11 +1,5 @@
 // hmc_estimate_counts: K1 (E-step trellis, K = 1) -> K3 backward -> K4 estep_counts, per arena wave.
 
-struct EstepTrie {      // host-built flattened ForwardPatternTree + its device copy
-    DevBuf<int> d_root, d_child, d_data;
-    DevTrie dev = {};
-    void release() { d_root.release(); d_child.release(); d_data.release(); }
-};
-
 static int build_trie(hmc_ctx *ctx, EstepTrie &t, int Pc, const int32_t *start, const int64_t *al_off, const int8_t *alleles)
 {
     const int L = ctx->L, A = ctx->Amax;
@@ -48,7 +42,7 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
     if (!ctx) return HMC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (Pc <= 0 || !start || !al_off || !alleles || !pg || count <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_estimate_counts: bad argument");
-    static EstepTrie trie;      // rebuilt per call; device buffers are reused
+    EstepTrie &trie = ctx->trie;      // rebuilt per call; device buffers are reused
     int rc = build_trie(ctx, trie, Pc, start, al_off, alleles);
     if (rc) return rc;
     CK(ctx->d_counts.ensure((size_t) 2 * Pc));
@@ -57,9 +51,9 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
     CK(cudaMemcpyAsync(ctx->d_pgin.p, pg, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
     const bool scaled = (flags & HMC_FLAG_SCALED) != 0;
     if (pg_exp) { CK(ctx->d_pgexp.ensure(count)); CK(cudaMemcpyAsync(ctx->d_pgexp.p, pg_exp, sizeof(int) * count, cudaMemcpyHostToDevice, ctx->stream)); }
-    static DevBuf<int> d_bexp, d_eflags;
-    static DevBuf<unsigned char> d_escr;
-    static DevBuf<EstepScratch> d_edesc;
+    DevBuf<int> &d_bexp = ctx->d_bexp, &d_eflags = ctx->d_eflags;
+    DevBuf<unsigned char> &d_escr = ctx->d_escr;
+    DevBuf<EstepScratch> &d_edesc = ctx->d_edesc;
     CK(d_eflags.ensure(4));
 
     auto after = [&](const FwdParams &fp, int n_wave, const std::vector<int> &, int &launches) -> int {
