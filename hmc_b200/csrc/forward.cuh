@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             const double al = in_cache ? ci_alpha[s] : gi_alpha[s];
                             if (al > 0.0) {     // HaploBuilder.cpp:237
                                 live[q] = true;
-                                ea[q] = __ldg(succ16 + (size_t) pa * A + x);
-                                eb[q] = __ldg(succ16 + (size_t) pb * A + y);
+                                ea[q] = __ldcg(succ16 + (size_t) pa * A + x);     // L2 only: the 150 MB table would only evict the lists and hash from L1
+                                eb[q] = __ldcg(succ16 + (size_t) pb * A + y);
                             }
                         }
                     }

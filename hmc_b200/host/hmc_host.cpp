@@ -229,17 +229,38 @@ struct Miner {
         }
     }
 
-    struct Arena { std::vector<int32_t> id; std::vector<double> fr; };
+    // stack of matching states; grows without initialising (std::vector::resize would zero-fill every stripe)
+    template <typename T>
+    struct RawVec {
+        T *p = nullptr;
+        size_t n = 0, cap = 0;
+        RawVec() {}
+        RawVec(const RawVec &) = delete;
+        RawVec &operator=(const RawVec &) = delete;
+        ~RawVec() { free(p); }
+        size_t size() const { return n; }
+        void resize(size_t m)
+        {
+            if (m > cap) { cap = std::max(m, cap * 2 + 1024); p = (T *) realloc(p, cap * sizeof(T)); if (!p) throw HmcError("out of host memory while mining"); }
+            n = m;
+        }
+        T &operator[](size_t i) { return p[i]; }
+        const T &operator[](size_t i) const { return p[i]; }
+        T *begin() { return p; }
+        void assign(const std::vector<T> &v) { resize(v.size()); if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T)); }
+    };
+    struct Arena { RawVec<int32_t> id; RawVec<double> fr; };
 
     struct Frame { double freq; size_t off, len; bool scanned; };
 
     // children of candidate (start, path[0..len), freq, ms) at locus e = start + len; returns per-allele frames
-    void extend(Arena &ar, int e, const Frame &parent, int plen, std::vector<Frame> &out) const
+    void extend(Arena &ar, int e, const Frame &parent, int plen, Frame *out) const
     {
         const int A = g.n_alleles[e];
-        out.assign(A, Frame{0.0, 0, 0, false});
+        for (int j = 0; j < A; ++j) out[j] = Frame{0.0, 0, 0, false};
         const bool full = (plen == 0) || parent.len == 0;       // checkFrequency: rescan everything (PatternManager.cpp:197-199)
-        std::vector<double> total(A, 0.0);
+        double total[HMC_MAX_ALLELES];
+        for (int j = 0; j < A; ++j) total[j] = 0.0;
         if (!use_samples) {
             const int N = g.N;
             const int8_t *a0 = &g0[(size_t) e * N], *a1 = &g1[(size_t) e * N];
@@ -250,18 +271,10 @@ struct Miner {
                 return;
             }
             const size_t n_in = full ? (size_t) N : parent.len;
-            // one sweep, A output lists laid out one after the other: count first, then fill
-            std::vector<size_t> cnt(A, 0);
-            for (size_t q = 0; q < n_in; ++q) {
-                const int i = full ? (int) q : ar.id[parent.off + q];
-                const int x = a0[i], y = a1[i];
-                if (x < 0 || y < 0) { for (int j = 0; j < A; ++j) ++cnt[j]; }
-                else { ++cnt[x]; if (y != x) ++cnt[y]; }
-            }
-            size_t base = ar.id.size();
-            size_t tot = 0;
-            for (int j = 0; j < A; ++j) { out[j].off = base + tot; tot += cnt[j]; out[j].len = 0; }
-            ar.id.resize(base + tot); ar.fr.resize(base + tot);
+            // one sweep: child j's list gets its own stripe of n_in entries on the arena stack (an individual matches a child at most once)
+            const size_t base = ar.id.size();
+            for (int j = 0; j < A; ++j) { out[j].off = base + (size_t) j * n_in; out[j].len = 0; }
+            ar.id.resize(base + (size_t) A * n_in); ar.fr.resize(base + (size_t) A * n_in);
             for (size_t q = 0; q < n_in; ++q) {
                 const int i = full ? (int) q : ar.id[parent.off + q];
                 const double pf = full ? 1.0 : ar.fr[parent.off + q];
@@ -287,15 +300,9 @@ struct Miner {
             const int8_t *hh = &sh[(size_t) e * n];
             if (full && plen > 0) { for (int j = 0; j < A; ++j) out[j] = Frame{0.0 / samples.total_weight, ar.id.size(), 0, true}; return; }
             const size_t n_in = full ? n : parent.len;
-            std::vector<size_t> cnt(A, 0);
-            for (size_t q = 0; q < n_in; ++q) {
-                const int i = full ? (int) q : ar.id[parent.off + q];
-                const int x = hh[i];
-                if (x < 0) { for (int j = 0; j < A; ++j) ++cnt[j]; } else ++cnt[x];
-            }
-            size_t base = ar.id.size(), tot = 0;
-            for (int j = 0; j < A; ++j) { out[j].off = base + tot; tot += cnt[j]; out[j].len = 0; }
-            ar.id.resize(base + tot); ar.fr.resize(base + tot);
+            const size_t base = ar.id.size();
+            for (int j = 0; j < A; ++j) { out[j].off = base + (size_t) j * n_in; out[j].len = 0; }
+            ar.id.resize(base + (size_t) A * n_in); ar.fr.resize(base + (size_t) A * n_in);
             for (size_t q = 0; q < n_in; ++q) {
                 const int i = full ? (int) q : ar.id[parent.off + q];
                 const int x = hh[i];
@@ -310,7 +317,7 @@ struct Miner {
     void visit(Arena &ar, PatternSet &out, int start, std::vector<int8_t> &path, const Frame &me, double prefix, double tp) const
     {
         const int len = (int) path.size(), e = start + len, L = g.L;
-        std::vector<Frame> kids;
+        Frame kids[HMC_MAX_ALLELES];
         const size_t mark = ar.id.size();
         bool extended = false;
         if (me.freq >= min_freq || len < min_len[start]) {
@@ -321,7 +328,7 @@ struct Miner {
         }
         if (extended) {
             const double *af = &g.allele_freq[(size_t) e * g.Amax];
-            for (int j = (int) kids.size() - 1; j >= 0; --j) {
+            for (int j = g.n_alleles[e] - 1; j >= 0; --j) {
                 if (!(af[j] > 0)) continue;
                 Pattern t;
                 const double pf = me.freq;
@@ -354,7 +361,8 @@ void PatternManager::searchPattern(bool by_num, int max_num)
         Miner miner(g, *m_builder.samples(), m_min_freq, m_min_len, m_max_len);
         std::vector<PatternSet> per_start(L);
         const int threads = hw_threads(m_threads);
-        std::vector<Miner::Arena> arenas(threads);
+        std::vector<Miner::Arena> arenas_store(threads);
+        Miner::Arena *arenas = arenas_store.data();
         parallel_for(L, threads, [&](int k, int t) {
             const int start = L - 1 - k;                // heaviest (longest) walks are not special; any order works
             std::vector<int8_t> path;
@@ -389,11 +397,11 @@ void PatternManager::searchPattern(bool by_num, int max_num)
             const int len = (int) pc.path.size(), e = pc.start + len;
             if (pc.fr.freq >= m_min_freq || len < m_min_len[pc.start]) {
                 if (e < L && len < m_max_len[pc.start]) {
-                    ar.id = pc.id; ar.fr = pc.f;
+                    ar.id.assign(pc.id); ar.fr.assign(pc.f);
                     Miner::Frame me{pc.fr.freq, 0, pc.id.size(), false};
-                    std::vector<Miner::Frame> kids;
+                    Miner::Frame kids[HMC_MAX_ALLELES];
                     miner.extend(ar, e, me, len, kids);
-                    for (int j = 0; j < (int) kids.size(); ++j) {
+                    for (int j = 0; j < g.n_alleles[e]; ++j) {
                         if (!(g.allele_freq[(size_t) e * g.Amax + j] > 0)) continue;
                         Cand c;
                         c.start = pc.start; c.path = pc.path; c.path.push_back((int8_t) j);
@@ -436,8 +444,11 @@ void PatternManager::findPatternByFreq(double min_freq, int min_len, int max_len
     max_len = std::max(max_len, min_len);
     setLens(min_len, max_len);
     m_min_freq = min_freq;
+    const double t0 = now_s();
     searchPattern(false, 0);
+    const double t1 = now_s();
     initialize();
+    if (getenv("HMC_B200_HOST_TIMING")) fprintf(stderr, "[host] searchPattern %.3f s, initialize %.3f s, patterns %d\n", t1 - t0, now_s() - t1, size());
 }
 
 void PatternManager::findPatternByNum(int max_num, int min_len, int max_len)
