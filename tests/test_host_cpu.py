@@ -85,3 +85,25 @@ def test_normalise_counts_matches_reference_rule():
     # HaploBuilder.cpp:317-331: clamp to N, freq <= prefix, /N, tp = freq/prefix (or freq/N), tp <= 1
     assert np.allclose(nf, [0, 3 / 40, 1.0, 2 / 40, 0.5 / 40]) and np.allclose(npf, [0, 0.1, 1.0, 0.05, 0.0125])
     assert np.allclose(tp, [0, 0.75, 1.0, 1.0, 1.0])
+
+
+def test_phase_reader_variants(tmp_path):
+    """HaploFile.cpp:54-153: optional 'P' line, blanks between the type characters, '-' / '?' as missing, 'M' loci with <= 0 as missing,
+    ids starting with '#' or a digit."""
+    p1 = tmp_path / "a.phase"
+    p1.write_text("3\n4\nS S M M\n1abc\n0 1 12 7\n1 1 12 -1\nx\n? 0 7 7\n- 1 0 12\ny\n0 0 12 12\n1 0 7 7\n")
+    hm = HaploModel()
+    hm.load_phase(str(p1))
+    idx, na, af = hm.panel()
+    assert idx.shape == (3, 2, 4) and list(na) == [2, 2, 2, 2]
+    assert idx[0].tolist() == [[0, 1, 1, 0], [1, 1, 1, -1]]         # symbols sorted: '0'<'1', 7<12
+    assert idx[1].tolist() == [[-1, 0, 0, 0], [-1, 1, -1, 1]]       # '?', '-', 0 and -1 are missing
+    assert abs(af[2, 0] - 2 / 5) < 1e-15 and abs(af[2, 1] - 3 / 5) < 1e-15
+    hm.close()
+    p2 = tmp_path / "b.phase"
+    p2.write_text("2\n3\nP 10 20 30\nSSS\n#7\n0 1 0\n1 1 0\nq\n1 0 0\n1 0 1\n")
+    hm = HaploModel()
+    hm.load_phase(str(p2))
+    idx2, na2, _ = hm.panel()
+    assert idx2.tolist() == [[[0, 1, 0], [1, 1, 0]], [[1, 0, 0], [1, 0, 1]]] and list(na2) == [2, 2, 2]
+    hm.close()
