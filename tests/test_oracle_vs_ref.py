@@ -50,3 +50,26 @@ def test_live_reference_run(tmp_path, kw, kind, ref_opts, opts):
         assert a["pg"] == b["pg"] and np.array_equal(a["prior"], np.array(b["prior"]))
         for k in range(a["n"]):
             assert np.array_equal(a["haps"][k], b["haps"][k])
+
+
+def test_config0_c1_200x100_defaults(tmp_path):
+    """BASELINE.json configs[0]: 200 individuals x 100 SNPs, default options -- oracle port == reference binary, bit for bit."""
+    g = make_panel(200, 100, founders=8, seed=1)
+    phase = str(tmp_path / "c1.phase")
+    dump = str(tmp_path / "c1.dump")
+    write_phase(phase, g, kind="S")
+    subprocess.check_call([REF, phase, "--dump", dump, "--out-suffix", "none", "-d", "1"], stderr=subprocess.DEVNULL)
+    d = refdump.load(dump)
+    o = Oracle(d["geno"])
+    o.find_patterns()
+    m, r = o.export_model(), d["iters"][0]["patterns"]
+    assert m["P"] == r["P"] == 49878
+    for k in ("start", "end", "freq", "prefix", "tp", "succ", "heads"):
+        assert np.array_equal(m[k], r[k]), k
+    assert o.resolve_all() == d["iters"][0]["ll"]
+    assert o.counters() == d["iters"][0]["counters"]
+    for i in range(200):
+        a, b = o.individual(i), d["iters"][0]["inds"][i]
+        assert a["pg"] == b["pg"] and np.array_equal(a["prior"], np.array(b["prior"]))
+        for k in range(a["n"]):
+            assert np.array_equal(a["haps"][k], b["haps"][k])
