@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "forward.cuh"
 #include "forward_warp.cuh"
+#include "forward_flat.cuh"
 #include "traceback.cuh"
 #include "estep.cuh"
 
@@ -108,6 +109,7 @@ struct hmc_ctx {
     DevBuf<EstepScratch> d_edesc;
     DevBuf<int> d_pgexp;
 
+    struct FlatPool *flat = nullptr;
     int64_t counters[HMC_CNT_N] = {};
     float kernel_ms[4] = {};
 
@@ -305,7 +307,7 @@ static int pick_threads(const hmc_ctx *ctx)
     const char *env = getenv("HMC_B200_THREADS");
     int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
     if (nt == 0) nt = 128;
-    if (nt != 32 && nt != 33 && nt != 64 && nt != 128 && nt != 256) nt = 128;
+    if (nt != 32 && nt != 33 && nt != 64 && nt != 128 && nt != 256) nt = 128;    // (1 = level-synchronous path; its fallback uses 128)
     return nt;
 }
 
@@ -437,6 +439,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     return HMC_OK;
 }
 
+#include "flat_capi.inl"
+
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -474,6 +478,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
     ctx->trie.release(); ctx->d_bexp.release(); ctx->d_eflags.release(); ctx->d_escr.release(); ctx->d_edesc.release(); ctx->d_cycles.release();
+    if (ctx->flat) { ctx->flat->release(); delete ctx->flat; }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -594,6 +599,17 @@ int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned f
     CK(ctx->d_prior.ensure((size_t) count * K)); CK(ctx->d_post.ensure((size_t) count * K));
     CK(ctx->d_haps.ensure((size_t) count * K * 2 * L));
     ctx->r_first = first; ctx->r_count = count; ctx->r_K = K;
+    {   // level-synchronous path (threads == 1 or HMC_B200_FLAT=1); falls back to the per-individual kernel when a capacity is exceeded
+        const char *env = getenv("HMC_B200_FLAT");
+        if (ctx->threads_opt == 1 || (env && atoi(env) == 1 && ctx->threads_opt == 0)) {
+            if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
+            if (!ctx->have_model) return ctx->fail(HMC_ERR_INVALID, "hmc_set_model has not been called");
+            if (first < 0 || first + count > ctx->N) return ctx->fail(HMC_ERR_INVALID, "individual range [%d,%d) outside the panel", first, first + count);
+            if (!ctx->flat) ctx->flat = new FlatPool;
+            const int rc = run_flat(ctx, *ctx->flat, first, count, K, flags);
+            if (rc <= 0) return rc;
+        }
+    }
     return run_waves(ctx, first, count, K, flags, 0, [](const FwdParams &, int, const std::vector<int> &, int &) { return 0; });
 }
 

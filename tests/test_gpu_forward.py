@@ -38,7 +38,7 @@ def run_device(d, o, K, threads=0, flags=FLAG_KEEP_TRELLIS):
     return dev, r
 
 
-@pytest.mark.parametrize("threads", [32, 64, 128, 256])
+@pytest.mark.parametrize("threads", [1, 32, 64, 128, 256])     # 1 = level-synchronous path
 @pytest.mark.parametrize("name", ["g1_clean", "g2_missing", "g3_multi", "g8_head2", "g9_k1"])
 def test_resolve_all_vs_reference_dump(name, threads):
     d = golden(name)
@@ -106,7 +106,7 @@ def test_missing_panel_spills_and_matches_oracle():
     o = Oracle(g)
     o.find_patterns()
     ll = o.resolve_all()
-    for threads in (32, 128):
+    for threads in (1, 32, 128):
         dev, r = run_device(g, o, 10, threads, flags=0)
         assert r["ll"] == ll
         c = dev.counters()
@@ -127,12 +127,15 @@ def test_scaled_long_panel():
     o.find_patterns()
     ll = o.resolve_all()
     assert np.isfinite(ll)
-    dev, r = run_device(g, o, 10, flags=FLAG_SCALED)
-    assert r["ll"] == ll
-    for i in range(24):
-        a = o.individual(i)
-        assert a["pg"] == r["pg"][i] and a["exp"] == r["exp"][i] and a["exp"] > 0
-        klist_equiv(r["prior"][i, :a["n"]], r["haps"][i, :a["n"]], a["prior"], a["haps"])
+    for threads in (0, 1):
+        dev, r = run_device(g, o, 10, threads, flags=FLAG_SCALED)
+        assert r["ll"] == ll
+        for i in range(24):
+            a = o.individual(i)
+            assert a["pg"] == r["pg"][i] and a["exp"] == r["exp"][i] and a["exp"] > 0
+            klist_equiv(r["prior"][i, :a["n"]], r["haps"][i, :a["n"]], a["prior"], a["haps"])
+        if threads == 0:
+            dev.close()
     # without scaling both underflow exactly like the reference
     o2 = Oracle(g, max_pattern_len=12)
     o2.find_patterns()
