@@ -15,6 +15,9 @@
 #include "forward.cuh"
 #include "forward_warp.cuh"
 #include "forward_flat.cuh"
+#include "mine.cuh"
+#include "automaton.cuh"
+#include <cub/cub.cuh>
 #include "traceback.cuh"
 #include "estep.cuh"
 
@@ -67,6 +70,10 @@ struct hmc_ctx {
     int N = 0, L = 0, Amax = 0, bits = 0, words = 0;
     double missing_frac = 0;
     DevBuf<u32> d_packed, d_linfo;
+    DevBuf<double> d_af;            // allele frequencies [L][Amax] (K5 mining)
+    int panel_serial = 0;           // bumped by every hmc_set_panel
+    struct MinePool *mine = nullptr;
+    struct AutPool *aut = nullptr;
     DevBuf<signed char> d_raw;      // staging of the unpacked genotypes (kept: cudaMalloc/cudaFree per call cost 100s of ms)
     DevBuf<int> d_order;
     std::vector<int> h_order, h_rank;
@@ -440,6 +447,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
 }
 
 #include "flat_capi.inl"
+#include "mine_capi.inl"
 
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -479,6 +487,9 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
     ctx->trie.release(); ctx->d_bexp.release(); ctx->d_eflags.release(); ctx->d_escr.release(); ctx->d_edesc.release(); ctx->d_cycles.release();
     if (ctx->flat) { ctx->flat->release(); delete ctx->flat; }
+    if (ctx->mine) { ctx->mine->release(); delete ctx->mine; }
+    if (ctx->aut) { ctx->aut->release(); delete ctx->aut; }
+    ctx->d_af.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -525,6 +536,9 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     CK(raw.ensure((size_t) N * 2 * L));
     CK(cudaMemcpyAsync(raw.p, geno, (size_t) N * 2 * L, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_linfo.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_af.ensure((size_t) L * Amax));
+    CK(cudaMemcpyAsync(ctx->d_af.p, allele_freq, sizeof(double) * (size_t) L * Amax, cudaMemcpyHostToDevice, ctx->stream));
+    ++ctx->panel_serial;
     CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
     const size_t nthr = (size_t) N * ctx->words;
     pack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, ctx->stream>>>(raw.p, N, L, ctx->bits, ctx->words, ctx->d_packed.p);
@@ -659,6 +673,94 @@ void hmc_normalise_counts(int Pc, int N, double *freq, double *prefix, double *t
         const double t = pf > 0 ? f / pf : f / N;
         if (tp) tp[i] = t < 1.0 ? t : 1.0;      // HaploPattern::setTransitionProb clamp, HaploPattern.h:47
     }
+}
+
+int hmc_mine_patterns(hmc_ctx *ctx, int n_samples, const int8_t *sample_haps, const double *sample_weights, double total_weight,
+                      double min_freq, const int32_t *min_len, const int32_t *max_len, int64_t *out_P, int64_t *out_n_alleles)
+{
+    if (!ctx || !min_len || !max_len || !out_P || !out_n_alleles || n_samples < 0 || (n_samples > 0 && (!sample_haps || !sample_weights)))
+        return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_mine_patterns: bad argument") : HMC_ERR_INVALID;
+    if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->mine) ctx->mine = new MinePool;
+    const int rc = run_mine(ctx, *ctx->mine, n_samples, sample_haps, sample_weights, total_weight, min_freq, min_len, max_len);
+    if (rc) return rc;
+    *out_P = ctx->mine->P; *out_n_alleles = ctx->mine->n_alleles;
+    return HMC_OK;
+}
+
+int hmc_fetch_patterns(hmc_ctx *ctx, int32_t *start, int32_t *end, double *freq, double *prefix_freq, double *tp, int64_t *al_off, int8_t *alleles)
+{
+    if (!ctx || !start || !end || !freq || !prefix_freq || !tp || !al_off || !alleles) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_fetch_patterns: bad argument") : HMC_ERR_INVALID;
+    if (!ctx->mine) return ctx->fail(HMC_ERR_INVALID, "hmc_fetch_patterns before hmc_mine_patterns");
+    MinePool &mp = *ctx->mine;
+    CK(cudaSetDevice(ctx->device));
+    const size_t P = (size_t) mp.P;
+    if (P == 0) { al_off[0] = 0; return HMC_OK; }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(start, mp.o_start.p, 4 * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(end, mp.o_end.p, 4 * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(freq, mp.o_freq.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(prefix_freq, mp.o_prefix.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(tp, mp.o_tp.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(al_off, mp.o_aloff.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(alleles, mp.o_al.p, (size_t) mp.n_alleles, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return HMC_OK;
+}
+
+int hmc_map_patterns(hmc_ctx *ctx, const hmc_pattern_rec **records, const int8_t **alleles)
+{
+    if (!ctx || !records || !alleles) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_map_patterns: bad argument") : HMC_ERR_INVALID;
+    if (!ctx->mine) return ctx->fail(HMC_ERR_INVALID, "hmc_map_patterns before hmc_mine_patterns");
+    MinePool &mp = *ctx->mine;
+    CK(cudaSetDevice(ctx->device));
+    const size_t rb = ((size_t) mp.P * sizeof(hmc_pattern_rec) + 255) & ~(size_t) 255, total = rb + (size_t) mp.n_alleles + 256;
+    if (total > mp.pin_bytes) {
+        if (mp.pin) cudaFreeHost(mp.pin);
+        mp.pin = nullptr; mp.pin_bytes = 0;
+        const size_t cap = total + total / 2;
+        CK(cudaHostAlloc(&mp.pin, cap, cudaHostAllocDefault));
+        mp.pin_bytes = cap;
+    }
+    if (!mp.pin_valid && mp.P > 0) {
+        CK(cudaMemcpyAsync(mp.pin, mp.o_rec.p, (size_t) mp.P * sizeof(hmc_pattern_rec), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync((char *) mp.pin + rb, mp.o_al.p, (size_t) mp.n_alleles, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        mp.pin_valid = true;
+    }
+    *records = (const hmc_pattern_rec *) mp.pin;
+    *alleles = (const int8_t *) ((char *) mp.pin + rb);
+    return HMC_OK;
+}
+
+int hmc_build_automaton(hmc_ctx *ctx, int head_len, int32_t *out_n_heads)
+{
+    if (!ctx) return HMC_ERR_INVALID;
+    if (!ctx->mine) return ctx->fail(HMC_ERR_INVALID, "hmc_build_automaton before hmc_mine_patterns");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->aut) ctx->aut = new AutPool;
+    return run_build_automaton(ctx, *ctx->mine, *ctx->aut, head_len, out_n_heads);
+}
+
+int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads)
+{
+    if (!ctx || !ctx->have_model) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_fetch_automaton: no model on the device") : HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (succ) CK(cudaMemcpyAsync(succ, ctx->dm.succ, sizeof(int) * (size_t) ctx->dm.P * ctx->dm.Amax, cudaMemcpyDeviceToHost, ctx->stream));
+    if (heads && ctx->dm.n_heads > 0) CK(cudaMemcpyAsync(heads, ctx->dm.heads, sizeof(int) * ctx->dm.n_heads, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HMC_OK;
+}
+
+int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list)
+{
+    if (!ctx || !ctx->mine) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_get_mine_stats before hmc_mine_patterns") : HMC_ERR_INVALID;
+    if (ms) *ms = ctx->mine->ms + (ctx->aut ? ctx->aut->ms : 0.0f);
+    if (nodes) *nodes = ctx->mine->nodes;
+    if (levels) *levels = ctx->mine->levels;
+    if (max_list) *max_list = ctx->mine->max_list;
+    return HMC_OK;
 }
 
 int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N])

@@ -21,7 +21,8 @@ CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps"
 EXPORTS = [
     "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",
     "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
-    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis",
+    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns",
+    "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats",
 ]
 
 
@@ -53,6 +54,12 @@ def lib():
         L.hmc_estimate_counts_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p)]
         L.hmc_normalise_counts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hmc_normalise_counts.restype = None
+        L.hmc_mine_patterns.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.hmc_fetch_patterns.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.hmc_build_automaton.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+        L.hmc_fetch_automaton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmc_get_mine_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.hmc_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_trellis.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
@@ -166,6 +173,44 @@ class DeviceBuilder:
         f = np.array(freq, np.float64); pf = np.array(prefix, np.float64); tp = np.zeros_like(f)
         lib().hmc_normalise_counts(len(f), N, _p(f), _p(pf), _p(tp))
         return f, pf, tp
+
+    def mine_patterns(self, min_freq: float, min_len, max_len, samples=None, weights=None, total_weight: float = 0.0) -> dict:
+        """PatternManager::searchPattern on the device (K5).  samples [n][L] int8 + weights [n] select the sampling branch;
+        min_len / max_len: scalars or per-start arrays [L].  Returns the pattern list in the reference's id order."""
+        L = self.L
+        mn = np.ascontiguousarray(np.broadcast_to(np.asarray(min_len, np.int32), (L,)))
+        mx = np.ascontiguousarray(np.broadcast_to(np.asarray(max_len, np.int32), (L,)))
+        n = 0
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.int8)
+            weights = np.ascontiguousarray(weights, np.float64)
+            n = samples.shape[0]
+            assert samples.shape == (n, L) and weights.shape == (n,)
+        P, na = C.c_int64(), C.c_int64()
+        self._ck(lib().hmc_mine_patterns(self._h, n, _p(samples), _p(weights), float(total_weight), float(min_freq), _p(mn), _p(mx), C.byref(P), C.byref(na)))
+        P, na = P.value, na.value
+        r = dict(P=P, start=np.zeros(P, np.int32), end=np.zeros(P, np.int32), freq=np.zeros(P), prefix=np.zeros(P), tp=np.zeros(P),
+                 al_off=np.zeros(P + 1, np.int64), alleles=np.zeros(max(na, 1), np.int8))
+        self._ck(lib().hmc_fetch_patterns(self._h, _p(r["start"]), _p(r["end"]), _p(r["freq"]), _p(r["prefix"]), _p(r["tp"]), _p(r["al_off"]), _p(r["alleles"])))
+        r["alleles"] = r["alleles"][:na]
+        return r
+
+    def build_automaton(self, head_len: int = 1) -> dict:
+        """PatternManager::initialize on the device over the last mined list; the model is installed in the context."""
+        nh = C.c_int32()
+        self._ck(lib().hmc_build_automaton(self._h, head_len, C.byref(nh)))
+        return dict(n_heads=nh.value)
+
+    def fetch_automaton(self, P: int, n_heads: int) -> dict:
+        succ = np.zeros((P, self.Amax), np.int32)
+        heads = np.zeros(max(n_heads, 1), np.int32)
+        self._ck(lib().hmc_fetch_automaton(self._h, _p(succ), _p(heads)))
+        return dict(succ=succ, heads=heads[:n_heads])
+
+    def mine_stats(self) -> dict:
+        ms, nodes, levels, mx = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(lib().hmc_get_mine_stats(self._h, C.byref(ms), C.byref(nodes), C.byref(levels), C.byref(mx)))
+        return dict(ms=ms.value, nodes=nodes.value, levels=levels.value, max_list=mx.value)
 
     def counters(self) -> dict:
         out = np.zeros(8, np.int64)

@@ -32,6 +32,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p] + ([C.c_char_p] if name == "hmch_load_phase" else [])
         L.hmch_set_panel_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p]
         L.hmch_set_options.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double] + [C.c_int] * 9
+        L.hmch_set_device_mining.argtypes = [C.c_void_p, C.c_int]
+        L.hmch_mined_on_device.argtypes = [C.c_void_p]
         L.hmch_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
         L.hmch_get_panel.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.hmch_resolve_all.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -52,7 +54,8 @@ class HaploModel:
     """HaploModel with the CLI defaults of HMC.cpp:35-47 (MV, min-freq-abs 1.5, max-pattern-len 30, sample-size 10, 1 iteration)."""
 
     DEFAULTS = dict(model="MV", min_freq=-1.0, min_freq_abs=1.5, num_patterns=-1, min_pattern_len=1, max_pattern_len=30, mc_order=1,
-                    max_iteration=1, sample_size=10, exact_estimate=False, scaled=False, host_threads=0)
+                    max_iteration=1, sample_size=10, exact_estimate=False, scaled=False, host_threads=0,
+                    device_mining=-1)      # pattern search: 1 device kernels, 0 host threads, -1 device when a B200 context exists
 
     def __init__(self, device: int = 0, arena_bytes: int = 0, threads: int = 0, **opts):
         err = C.create_string_buffer(512)
@@ -85,6 +88,10 @@ class HaploModel:
         self._ck(lib().hmch_set_options(self._h, o["model"].encode(), o["min_freq"], o["min_freq_abs"], o["num_patterns"], o["min_pattern_len"],
                                         o["max_pattern_len"], o["mc_order"], o["max_iteration"], o["sample_size"], int(o["exact_estimate"]),
                                         int(o["scaled"]), o["host_threads"]))
+        self._ck(lib().hmch_set_device_mining(self._h, int(o["device_mining"])))
+
+    def mined_on_device(self) -> bool:
+        return bool(lib().hmch_mined_on_device(self._h))
 
     def _dims(self):
         n, l, a = C.c_int(), C.c_int(), C.c_int()

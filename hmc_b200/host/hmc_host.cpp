@@ -356,6 +356,9 @@ void PatternManager::searchPattern(bool by_num, int max_num)
 {
     const GenoData &g = *m_builder.genos();
     const int L = g.L;
+    last_mine_on_device = false;
+    m_dev_list_fresh = false;
+    if (!by_num && m_device_mining != 0 && searchPatternDevice()) { last_mine_on_device = true; m_dev_list_fresh = true; return; }
     m_patterns.clear();
     if (!by_num) {
         Miner miner(g, *m_builder.samples(), m_min_freq, m_min_len, m_max_len);
@@ -436,6 +439,46 @@ void PatternManager::searchPattern(bool by_num, int max_num)
     }
 }
 
+// The same search on the device (K5, csrc/mine.cuh): identical ids and bit-identical frequencies.
+bool PatternManager::searchPatternDevice()
+{
+    const char *env = getenv("HMC_B200_HOST_MINING");
+    if (env && atoi(env) != 0) return false;
+    hmc_ctx *c = nullptr;
+    try { c = m_builder.ctx(); }
+    catch (const HmcError &) { if (m_device_mining > 0) throw; return false; }
+    m_builder.uploadPanel();
+    const HaploData &sm = *m_builder.samples();
+    const int n = (int) sm.w.size();
+    int64_t P = 0, na = 0;
+    const double t0 = now_s();
+    int rc = hmc_mine_patterns(c, n, n ? sm.h.data() : nullptr, n ? sm.w.data() : nullptr, sm.total_weight, m_min_freq, m_min_len.data(), m_max_len.data(), &P, &na);
+    if (rc < 0) throw HmcError(std::string("hmc_mine_patterns: ") + hmc_last_error(c));
+    const double t1 = now_s();
+    const hmc_pattern_rec *recs = nullptr;
+    const int8_t *als = nullptr;
+    rc = hmc_map_patterns(c, &recs, &als);
+    if (rc < 0) throw HmcError(std::string("hmc_map_patterns: ") + hmc_last_error(c));
+    const double t2 = now_s();
+    static_assert(sizeof(Pattern) == sizeof(hmc_pattern_rec) && offsetof(Pattern, al) == offsetof(hmc_pattern_rec, al) &&
+                  offsetof(Pattern, transition_prob) == offsetof(hmc_pattern_rec, transition_prob), "Pattern must mirror hmc_pattern_rec");
+    m_patterns.pats.resize((size_t) P);
+    m_patterns.alleles.resize((size_t) na);
+    const int threads = hw_threads(m_threads), chunks = std::max(1, std::min(threads * 4, (int) (P / 65536) + 1));
+    parallel_for(chunks, threads, [&](int k, int) {
+        const size_t p0 = (size_t) P * k / chunks, p1 = (size_t) P * (k + 1) / chunks, a0 = (size_t) na * k / chunks, a1 = (size_t) na * (k + 1) / chunks;
+        if (p1 > p0) memcpy((void *) (m_patterns.pats.data() + p0), recs + p0, (p1 - p0) * sizeof(Pattern));
+        if (a1 > a0) memcpy(m_patterns.alleles.data() + a0, als + a0, a1 - a0);
+    });
+    if (getenv("HMC_B200_HOST_TIMING")) {
+        double ms = 0; int64_t nodes = 0, levels = 0, mx = 0;
+        hmc_get_mine_stats(c, &ms, &nodes, &levels, &mx);
+        fprintf(stderr, "[host] device mining: call %.3f s (kernels %.1f ms, %lld trie nodes, %lld levels, largest level list %lld), fetch %.3f s, unpack %.3f s\n",
+                t1 - t0, ms, (long long) nodes, (long long) levels, (long long) mx, t2 - t1, now_s() - t2);
+    }
+    return true;
+}
+
 void PatternManager::findPatternByFreq(double min_freq, int min_len, int max_len)
 {
     const int L = m_builder.genotype_len();
@@ -448,7 +491,8 @@ void PatternManager::findPatternByFreq(double min_freq, int min_len, int max_len
     searchPattern(false, 0);
     const double t1 = now_s();
     initialize();
-    if (getenv("HMC_B200_HOST_TIMING")) fprintf(stderr, "[host] searchPattern %.3f s, initialize %.3f s, patterns %d\n", t1 - t0, now_s() - t1, size());
+    if (getenv("HMC_B200_HOST_TIMING")) fprintf(stderr, "[host] searchPattern %.3f s (%s), initialize %.3f s (%s), patterns %d\n", t1 - t0, last_mine_on_device ? "device" : "host threads", now_s() - t1,
+                                                last_automaton_on_device ? "device" : "host threads", size());
 }
 
 void PatternManager::findPatternByNum(int max_num, int min_len, int max_len)
@@ -488,6 +532,22 @@ void PatternManager::initialize()
     const GenoData &g = *m_builder.genos();
     const int L = g.L, A = std::max(g.Amax, 1), P = size();
     const int threads = hw_threads(m_threads);
+    const bool fresh = m_dev_list_fresh;
+    m_dev_list_fresh = false;
+    m_host_automaton_stale = false;
+    last_automaton_on_device = false;
+    if (fresh && P > 0 && !getenv("HMC_B200_HOST_AUTOMATON")) {
+        // the list came straight from the device miner and is still there: build and install the automaton in place (K6)
+        hmc_ctx *c = m_builder.ctx();
+        int32_t nh = 0;
+        if (hmc_build_automaton(c, head_len(), &nh) < 0) throw HmcError(std::string("hmc_build_automaton: ") + hmc_last_error(c));
+        m_dev_heads = nh;
+        m_succ.clear(); m_head_list.clear();
+        m_host_automaton_stale = true;
+        last_automaton_on_device = true;
+        m_builder.markModelClean();
+        return;
+    }
     m_head_list.clear();
     std::vector<std::vector<int32_t> > by_end(L + 1);
     for (int i = 0; i < P; ++i) {
@@ -534,6 +594,17 @@ void PatternManager::initialize()
         }
     });
     m_builder.markModelDirty();
+}
+
+void PatternManager::syncAutomaton() const
+{
+    if (!m_host_automaton_stale) return;
+    hmc_ctx *c = m_builder.ctx();
+    const int A = std::max(m_builder.genos()->Amax, 1);
+    m_succ.assign((size_t) size() * A, -1);
+    m_head_list.assign((size_t) m_dev_heads, -1);
+    if (hmc_fetch_automaton(c, m_succ.data(), m_head_list.data()) < 0) throw HmcError(std::string("hmc_fetch_automaton: ") + hmc_last_error(c));
+    m_host_automaton_stale = false;
 }
 
 void PatternManager::estimateFrequency()
@@ -586,6 +657,7 @@ void PatternManager::estimatePatterns()
     const int L = g.L, A = std::max(g.Amax, 1);
     PatternSet patterns, candidates;
     std::vector<int> seeds;
+    const std::vector<int32_t> &succ = successors();
     for (int i = 0; i < size(); ++i) {
         const Pattern &hp = m_patterns.pats[i];
         patterns.add(hp.start, m_patterns.al(hp), hp.length(), hp.frequency, hp.prefix_freq, hp.transition_prob);
@@ -593,7 +665,7 @@ void PatternManager::estimatePatterns()
             std::vector<int8_t> al(m_patterns.al(hp), m_patterns.al(hp) + hp.length());
             al.push_back(0);
             for (int j = 0; j < g.n_alleles[hp.end]; ++j) {
-                const int s = m_succ[(size_t) i * A + j];
+                const int s = succ[(size_t) i * A + j];
                 if (s < 0 || m_patterns.pats[s].start != hp.start) {    // unseen one-allele extension
                     al.back() = (int8_t) j;
                     seeds.push_back(patterns.add(hp.start, al.data(), (int) al.size(), hp.frequency, 1.0, 1.0));

@@ -89,19 +89,28 @@ class PatternManager {
     PatternSet m_patterns;
     double m_min_freq = 0;
     std::vector<int> m_min_len, m_max_len;
-    std::vector<int32_t> m_succ;        // [P][Amax]
-    std::vector<int32_t> m_head_list;
+    mutable std::vector<int32_t> m_succ;        // [P][Amax]
+    mutable std::vector<int32_t> m_head_list;
+    mutable bool m_host_automaton_stale = false;    // the automaton was built on the device (K6); host copies are fetched on demand
+    int m_dev_heads = 0;
+    bool m_dev_list_fresh = false;      // m_patterns is exactly the list of the last hmc_mine_patterns call
+    void syncAutomaton() const;
     int m_threads = 0;
+    int m_device_mining = -1;           // 1 device (K5), 0 host threads, -1 device when a B200 context can be created
 
 public:
     explicit PatternManager(HaploBuilder &hb) : m_builder(hb) {}
     const PatternSet &patterns() const { return m_patterns; }
-    const std::vector<int32_t> &successors() const { return m_succ; }
-    const std::vector<int32_t> &head_list() const { return m_head_list; }
+    const std::vector<int32_t> &successors() const { syncAutomaton(); return m_succ; }
+    const std::vector<int32_t> &head_list() const { syncAutomaton(); return m_head_list; }
+    bool last_automaton_on_device = false;
     int head_len() const { return m_min_len[0]; }
     int size() const { return (int) m_patterns.size(); }
     double min_freq() const { return m_min_freq; }
     void setThreads(int t) { m_threads = t; }
+    void setDeviceMining(int mode) { m_device_mining = mode; }
+    double last_mine_seconds = 0;       // wall time of the last searchPattern
+    bool last_mine_on_device = false;
 
     void findPatternByFreq(double min_freq, int min_len = 2, int max_len = 0);
     void findPatternByNum(int max_num, int min_len = 2, int max_len = 0);
@@ -114,6 +123,7 @@ public:
 protected:
     void setLens(int min_len, int max_len);
     void searchPattern(bool by_num, int max_num);
+    bool searchPatternDevice();     // hmc_mine_patterns; false when no device context is available in auto mode
     void initialize();              // PatternManager.cpp:293-318
     void extendPatterns(PatternSet &patterns, std::vector<int> &seeds, const PatternSet &last, const std::vector<int> &last_seeds);
 };
@@ -148,6 +158,7 @@ public:
     void setScaled(bool on) { m_flags = on ? (m_flags | HMC_FLAG_SCALED) : (m_flags & ~HMC_FLAG_SCALED); }
     unsigned flags() const { return m_flags; }
     void markModelDirty() { m_model_dirty = true; }
+    void markModelClean() { m_model_dirty = false; }     // the device built and installed the automaton itself (hmc_build_automaton)
 
     // Multi-GPU (one process per GPU): individuals [first, first+count) are this rank's; the collectives are supplied by the
     // launcher (torch.distributed / NCCL / MPI).  reduce_counts: in-place sum over ranks of n doubles.  gather: every rank

@@ -56,6 +56,9 @@ int hmch_set_options(void *p, const char *model, double min_freq, double min_fre
           m.min_pattern_len = min_len; m.max_pattern_len = max_len; m.mc_order = mc_order; m.max_iteration = max_iter; m.sample_size = sample_size;
           m.exact_estimate = exact != 0; m.setScaled(scaled != 0); m.patternManager().setThreads(host_threads));
 }
+// pattern search placement: 1 device (K5), 0 host threads, -1 device when a context can be created
+int hmch_set_device_mining(void *p, int mode) { Handle *h = (Handle *) p; GUARD(h->hm->patternManager().setDeviceMining(mode)); }
+int hmch_mined_on_device(void *p) { Handle *h = (Handle *) p; return h->hm->patternManager().last_mine_on_device ? 1 : 0; }
 void hmch_dims(void *p, int *N, int *L, int *Amax) { Handle *h = (Handle *) p; *N = h->input.N; *L = h->input.L; *Amax = h->input.Amax; }
 void hmch_get_panel(void *p, int8_t *idx, int32_t *n_alleles, double *allele_freq)
 {

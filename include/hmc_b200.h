@@ -119,6 +119,36 @@ int hmc_estimate_counts_device(hmc_ctx *ctx, int first, int count, unsigned flag
 /* HaploBuilder.cpp:317-331 on host arrays: clamp to N, freq <= prefix, divide by N, transition probability. */
 void hmc_normalise_counts(int Pc, int N, double *freq, double *prefix, double *tp);
 
+/* K5: the pattern search of the M-step, PatternManager::searchPattern with checkFrequencyWithExtension /
+ * getMatchingFrequency (PatternManager.cpp:100-291), for the frequency-threshold models (findPatternByFreq,
+ * findPatternBlock).  n_samples == 0: the genotype branch over the panel of hmc_set_panel (:156-179,205-251);
+ * n_samples > 0: the sampling branch over weighted sampled haplotypes (:180-191,252-263),
+ *   sample_haps [n_samples][L] allele indices (-1 missing), sample_weights [n_samples], total_weight = HaploData's.
+ * min_len / max_len [L]: per start locus (PatternManager.cpp:33-34).  Patterns come back in the reference's id order
+ * (release order of its depth-first stack) with bit-identical frequency, prefix_freq and transition_prob.
+ * Two calls: hmc_mine_patterns returns the sizes, hmc_fetch_patterns copies into caller buffers
+ *   start/end/freq/prefix_freq/tp [P], al_off [P+1], alleles [n_alleles]. */
+int hmc_mine_patterns(hmc_ctx *ctx, int n_samples, const int8_t *sample_haps, const double *sample_weights, double total_weight,
+                      double min_freq, const int32_t *min_len, const int32_t *max_len, int64_t *out_P, int64_t *out_n_alleles);
+int hmc_fetch_patterns(hmc_ctx *ctx, int32_t *start, int32_t *end, double *freq, double *prefix_freq, double *tp, int64_t *al_off,
+                       int8_t *alleles);
+/* The same list as records in page-locked host memory owned by the context (one D2H copy at link speed, no caller
+ * buffers): valid until the next hmc_mine_patterns / hmc_ctx_destroy.  `al` is the offset of the allele string. */
+typedef struct hmc_pattern_rec {
+    int32_t start, end;
+    int64_t al;
+    double frequency, prefix_freq, transition_prob;
+} hmc_pattern_rec;
+int hmc_map_patterns(hmc_ctx *ctx, const hmc_pattern_rec **records, const int8_t **alleles);
+/* K6: PatternManager::initialize (PatternManager.cpp:293-318) over the list of the last hmc_mine_patterns call, on the
+ * device: successor table by longest trailing match with start >= the pattern's start (PatternTree.cpp:98-134), head
+ * list (:303-306); the result is installed as the context's model exactly as hmc_set_model would (no host round trip).
+ * hmc_fetch_automaton copies succ [P][Amax] and heads [n_heads] out for parity checks / export; either may be NULL. */
+int hmc_build_automaton(hmc_ctx *ctx, int head_len, int32_t *out_n_heads);
+int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads);
+/* Device time (ms, mining + automaton) and trie statistics of the last hmc_mine_patterns call; any pointer may be NULL. */
+int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list);
+
 /* Structural counters of the last resolve/estimate call (HMC_CNT_*), for parity and the roofline. */
 int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N]);
 /* Device time (ms, CUDA events) of the kernels of the last call: [0] forward, [1] traceback, [2] backward, [3] E-step. */

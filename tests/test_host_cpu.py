@@ -32,7 +32,7 @@ def test_mining_is_thread_count_independent():
     d = golden("g2_missing")
     ms = []
     for t in (1, 3, 8):
-        hm = HaploModel(host_threads=t)
+        hm = HaploModel(host_threads=t, device_mining=0)
         hm.load_phase(os.path.join(GOLDEN, "g2_missing.phase"))
         hm.build()
         ms.append(hm.export_model())
