@@ -252,6 +252,29 @@ def run_ours(args):
 
     cpu = cpu_baseline(shard, n_alleles, allele_freq, model, n_loci) if n_gpus == 1 else None      # reported at N = 1 only
 
+    # M-step leg (SURVEY 8d "report host M-step time beside them"): the pattern search + automaton build of this panel, on the device
+    # (K5 + K6, the genotype branch that builds the first model) and by the host-thread miner; results are bit-identical (tests/test_gpu_mine.py)
+    mstep = None
+    if n_gpus == 1:
+        min_freq = 1.5 / (2.0 * n_ind)
+        dev.mine_patterns(min_freq, 1, 30); dev.build_automaton(1)
+        t_begin = time.perf_counter()
+        mined = dev.mine_patterns(min_freq, 1, 30)
+        aut = dev.build_automaton(1)
+        t_dev = time.perf_counter() - t_begin
+        st = dev.mine_stats()
+        assert mined["P"] == model["P"] and np.array_equal(mined["freq"], model["freq"])
+        threads = os.cpu_count() or 8
+        hm0 = HaploModel(device=local, host_threads=threads, device_mining=0)
+        hm0.set_panel(g, kind)
+        t_begin = time.perf_counter()
+        hm0.build()
+        t_host = time.perf_counter() - t_begin
+        hm0.close()
+        mstep = {"what": "PatternManager::searchPattern + initialize for the first model of this panel (genotype branch)", "patterns": int(mined["P"]),
+                 "device_s": t_dev, "device_kernel_ms": st["ms"], "trie_nodes": st["nodes"], "list_entries_swept": st["swept"], "list_entries_written": st["written"],
+                 "host_threads_s": t_host, "host_threads": threads, "note": "device_s includes the D2H copy of the pattern list"}
+
     line = {
         "metric": "individual x locus phasing steps/sec per EM iteration", "value": value, "unit": "steps/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -270,6 +293,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "exact_epass": epass,
+        "mstep": mstep,
     }
     print(json.dumps(line))
     if world > 1:

@@ -753,13 +753,15 @@ int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads)
     return HMC_OK;
 }
 
-int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list)
+int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list, int64_t *swept, int64_t *written)
 {
     if (!ctx || !ctx->mine) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_get_mine_stats before hmc_mine_patterns") : HMC_ERR_INVALID;
     if (ms) *ms = ctx->mine->ms + (ctx->aut ? ctx->aut->ms : 0.0f);
     if (nodes) *nodes = ctx->mine->nodes;
     if (levels) *levels = ctx->mine->levels;
     if (max_list) *max_list = ctx->mine->max_list;
+    if (swept) *swept = ctx->mine->swept;
+    if (written) *written = ctx->mine->written;
     return HMC_OK;
 }
 

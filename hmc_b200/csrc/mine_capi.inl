@@ -33,6 +33,7 @@ struct MinePool {
     int panel_serial = -1;          // a0/a1 hold the transposed panel of this hmc_set_panel call
     float ms = 0;
     long long nodes = 0, levels = 0, max_list = 0;
+    long long swept = 0, written = 0;   // match-list entries read by the sweeps (count + fill) / written by the fill sweeps
 
     template <typename T>
     static cudaError_t regrow(T *&p, size_t old_n, size_t new_n)
@@ -127,7 +128,8 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     long long node_end = 0;
     int par = 0, epar = 0, prev_ext = 0;
     long long c0 = 0, n = L;            // the level whose nodes were just created (level 0: the roots)
-    mp.max_list = 0;
+    mp.max_list = 0; mp.swept = 0; mp.written = 0;
+    long long prev_in = 0;              // entries in the lists of the current parents
     for (int d = 0;; ++d) {
         level_begin.push_back(c0);
         node_end = c0 + n;
@@ -157,6 +159,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
             const unsigned gw = (unsigned) std::min<long long>(((long long) n_par * 32 + 255) / 256, (long long) ctx->sms * 32);
             if (samples) mine_sweep_kernel<true, true><<<gw, 256, 0, st>>>(m, n_par, par);
             else mine_sweep_kernel<false, true><<<gw, 256, 0, st>>>(m, n_par, par);
+            mp.swept += prev_in; mp.written += t.list_total;
         }
         if (d > 0) par ^= 1;
         epar ^= 1;
@@ -169,6 +172,8 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         if (samples) mine_sweep_kernel<true, false><<<gw, 256, 0, st>>>(m, (int) t.n_ext, par);
         else mine_sweep_kernel<false, false><<<gw, 256, 0, st>>>(m, (int) t.n_ext, par);
         prev_ext = (int) t.n_ext;
+        prev_in = d == 0 ? t.n_ext * (long long) n_items : t.list_total;
+        mp.swept += prev_in;
         c0 = node_end; n = t.n_child;
     }
     level_begin.push_back(node_end);

@@ -59,7 +59,7 @@ def lib():
         L.hmc_fetch_patterns.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.hmc_build_automaton.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
         L.hmc_fetch_automaton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.hmc_get_mine_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.hmc_get_mine_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_int64)] * 5
         L.hmc_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_trellis.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
@@ -208,9 +208,9 @@ class DeviceBuilder:
         return dict(succ=succ, heads=heads[:n_heads])
 
     def mine_stats(self) -> dict:
-        ms, nodes, levels, mx = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
-        self._ck(lib().hmc_get_mine_stats(self._h, C.byref(ms), C.byref(nodes), C.byref(levels), C.byref(mx)))
-        return dict(ms=ms.value, nodes=nodes.value, levels=levels.value, max_list=mx.value)
+        ms, nodes, levels, mx, sw, wr = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(lib().hmc_get_mine_stats(self._h, C.byref(ms), C.byref(nodes), C.byref(levels), C.byref(mx), C.byref(sw), C.byref(wr)))
+        return dict(ms=ms.value, nodes=nodes.value, levels=levels.value, max_list=mx.value, swept=sw.value, written=wr.value)
 
     def counters(self) -> dict:
         out = np.zeros(8, np.int64)

@@ -472,7 +472,7 @@ bool PatternManager::searchPatternDevice()
     });
     if (getenv("HMC_B200_HOST_TIMING")) {
         double ms = 0; int64_t nodes = 0, levels = 0, mx = 0;
-        hmc_get_mine_stats(c, &ms, &nodes, &levels, &mx);
+        hmc_get_mine_stats(c, &ms, &nodes, &levels, &mx, nullptr, nullptr);
         fprintf(stderr, "[host] device mining: call %.3f s (kernels %.1f ms, %lld trie nodes, %lld levels, largest level list %lld), fetch %.3f s, unpack %.3f s\n",
                 t1 - t0, ms, (long long) nodes, (long long) levels, (long long) mx, t2 - t1, now_s() - t2);
     }

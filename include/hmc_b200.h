@@ -146,8 +146,9 @@ int hmc_map_patterns(hmc_ctx *ctx, const hmc_pattern_rec **records, const int8_t
  * hmc_fetch_automaton copies succ [P][Amax] and heads [n_heads] out for parity checks / export; either may be NULL. */
 int hmc_build_automaton(hmc_ctx *ctx, int head_len, int32_t *out_n_heads);
 int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads);
-/* Device time (ms, mining + automaton) and trie statistics of the last hmc_mine_patterns call; any pointer may be NULL. */
-int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list);
+/* Device time (ms, mining + automaton) and trie statistics of the last hmc_mine_patterns call; any pointer may be NULL.
+ * swept / written: match-list entries read by the sweeps / written into child lists (the roofline's traffic model). */
+int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list, int64_t *swept, int64_t *written);
 
 /* Structural counters of the last resolve/estimate call (HMC_CNT_*), for parity and the roofline. */
 int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N]);
