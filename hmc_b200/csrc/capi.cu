@@ -683,9 +683,44 @@ int hmc_mine_patterns(hmc_ctx *ctx, int n_samples, const int8_t *sample_haps, co
     if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->mine) ctx->mine = new MinePool;
-    const int rc = run_mine(ctx, *ctx->mine, n_samples, sample_haps, sample_weights, total_weight, min_freq, min_len, max_len);
+    const int rc = run_mine(ctx, *ctx->mine, n_samples, sample_haps, nullptr, sample_weights, total_weight, min_freq, min_len, max_len);
     if (rc) return rc;
     *out_P = ctx->mine->P; *out_n_alleles = ctx->mine->n_alleles;
+    return HMC_OK;
+}
+
+int hmc_mine_patterns_resolved(hmc_ctx *ctx, int n_samples, const int32_t *rows, const double *sample_weights, double total_weight,
+                               double min_freq, const int32_t *min_len, const int32_t *max_len, int64_t *out_P, int64_t *out_n_alleles)
+{
+    if (!ctx || !min_len || !max_len || !out_P || !out_n_alleles || n_samples <= 0 || !rows || !sample_weights)
+        return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_mine_patterns_resolved: bad argument") : HMC_ERR_INVALID;
+    if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
+    if (ctx->r_count <= 0 || !ctx->d_haps.p) return ctx->fail(HMC_ERR_INVALID, "hmc_mine_patterns_resolved: no resolve results on the device");
+    const long long n_rows = (long long) ctx->r_count * ctx->r_K * 2;
+    for (int i = 0; i < n_samples; ++i) if (rows[i] < 0 || rows[i] >= n_rows) return ctx->fail(HMC_ERR_INVALID, "sample row %d outside the %lld result rows", rows[i], n_rows);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->mine) ctx->mine = new MinePool;
+    const int rc = run_mine(ctx, *ctx->mine, n_samples, nullptr, rows, sample_weights, total_weight, min_freq, min_len, max_len);
+    if (rc) return rc;
+    *out_P = ctx->mine->P; *out_n_alleles = ctx->mine->n_alleles;
+    return HMC_OK;
+}
+
+int hmc_result_dims(hmc_ctx *ctx, int32_t *count, int32_t *K)
+{
+    if (!ctx) return HMC_ERR_INVALID;
+    if (count) *count = ctx->r_count;
+    if (K) *K = ctx->r_K;
+    return HMC_OK;
+}
+
+int hmc_fetch_best_haps(hmc_ctx *ctx, int8_t *out_best)
+{
+    if (!ctx || !out_best || ctx->r_count <= 0) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_fetch_best_haps: no results to fetch") : HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const size_t row = (size_t) 2 * ctx->L;
+    CK(cudaMemcpy2DAsync(out_best, row, ctx->d_haps.p, row * ctx->r_K, row, ctx->r_count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return HMC_OK;
 }
 

@@ -288,4 +288,20 @@ __global__ void mine_transpose_kernel(const signed char *src, int n, int L, int 
     }
 }
 
+// sampled haplotypes taken from the result rows of the last resolve pass: a0[l][s] = haps[rows[s]][l]
+__global__ void mine_transpose_rows_kernel(const signed char *haps, const int *rows, int n, int L, signed char *a0)
+{
+    __shared__ signed char tile[32][33];
+    const int i0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, l = l0 + threadIdx.x;
+        if (i < n && l < L) tile[r][threadIdx.x] = haps[(size_t) rows[i] * L + l];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int l = l0 + r, i = i0 + threadIdx.x;
+        if (i < n && l < L) a0[(size_t) l * n + i] = tile[threadIdx.x][r];
+    }
+}
+
 }  // namespace hmc

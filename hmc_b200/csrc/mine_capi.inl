@@ -19,7 +19,7 @@ struct MinePool {
     DevBuf<MineTotals> tot;
     DevBuf<signed char> a0, a1, samples_raw;
     DevBuf<double> w;
-    DevBuf<int> min_len, max_len;
+    DevBuf<int> min_len, max_len, rows;
     // results
     DevBuf<int> o_start, o_end, o_node;
     DevBuf<double> o_freq, o_prefix, o_tp;
@@ -66,7 +66,7 @@ struct MinePool {
         nd = {}; node_cap = 0;
         for (int i = 0; i < 2; ++i) { list_id[i].release(); list_fr[i].release(); ext[i].release(); }
         need.release(); need_scan.release(); packed.release(); packed_scan.release(); cub_tmp.release(); tot.release();
-        a0.release(); a1.release(); samples_raw.release(); w.release(); min_len.release(); max_len.release();
+        a0.release(); a1.release(); samples_raw.release(); rows.release(); w.release(); min_len.release(); max_len.release();
         o_start.release(); o_end.release(); o_node.release(); o_freq.release(); o_prefix.release(); o_tp.release();
         o_len.release(); o_aloff.release(); o_P.release(); o_al.release(); o_rec.release();
         if (pin) cudaFreeHost(pin);
@@ -83,7 +83,7 @@ static int mine_scan(hmc_ctx *ctx, MinePool &mp, const long long *in, long long 
     return HMC_OK;
 }
 
-static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sample_haps, const double *sample_w, double total_weight,
+static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sample_haps, const int32_t *sample_rows, const double *sample_w, double total_weight,
                     double min_freq, const int32_t *min_len, const int32_t *max_len)
 {
     const int L = ctx->L, N = ctx->N;
@@ -95,10 +95,18 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     const dim3 tb(32, 8);
     const dim3 tg((unsigned) ((n_items + 31) / 32), (unsigned) ((L + 31) / 32));
     if (samples) {
-        CK(mp.samples_raw.ensure((size_t) n_items * L)); CK(mp.a0.ensure((size_t) n_items * L)); CK(mp.w.ensure(n_items));
-        CK(cudaMemcpyAsync(mp.samples_raw.p, sample_haps, (size_t) n_items * L, cudaMemcpyHostToDevice, st));
+        CK(grow(mp.a0, (size_t) n_items * L)); CK(grow(mp.w, (size_t) n_items));
         CK(cudaMemcpyAsync(mp.w.p, sample_w, sizeof(double) * n_items, cudaMemcpyHostToDevice, st));
-        mine_transpose_kernel<<<tg, tb, 0, st>>>(mp.samples_raw.p, n_items, L, 1, mp.a0.p, nullptr);
+        if (sample_rows) {      // rows of the haplotype results the last resolve pass left on the device
+            CK(grow(mp.rows, (size_t) n_items));
+            CK(cudaMemcpyAsync(mp.rows.p, sample_rows, sizeof(int) * n_items, cudaMemcpyHostToDevice, st));
+            mine_transpose_rows_kernel<<<tg, tb, 0, st>>>(ctx->d_haps.p, mp.rows.p, n_items, L, mp.a0.p);
+        }
+        else {
+            CK(grow(mp.samples_raw, (size_t) n_items * L));
+            CK(cudaMemcpyAsync(mp.samples_raw.p, sample_haps, (size_t) n_items * L, cudaMemcpyHostToDevice, st));
+            mine_transpose_kernel<<<tg, tb, 0, st>>>(mp.samples_raw.p, n_items, L, 1, mp.a0.p, nullptr);
+        }
         mp.panel_serial = -1;
     }
     else if (mp.panel_serial != ctx->panel_serial) {

@@ -360,6 +360,7 @@ void PatternManager::searchPattern(bool by_num, int max_num)
     m_dev_list_fresh = false;
     if (!by_num && m_device_mining != 0 && searchPatternDevice()) { last_mine_on_device = true; m_dev_list_fresh = true; return; }
     m_patterns.clear();
+    m_builder.materializeSamples();
     if (!by_num) {
         Miner miner(g, *m_builder.samples(), m_min_freq, m_min_len, m_max_len);
         std::vector<PatternSet> per_start(L);
@@ -440,10 +441,15 @@ void PatternManager::searchPattern(bool by_num, int max_num)
 }
 
 // The same search on the device (K5, csrc/mine.cuh): identical ids and bit-identical frequencies.
-bool PatternManager::searchPatternDevice()
+bool PatternManager::deviceMiningWanted() const
 {
     const char *env = getenv("HMC_B200_HOST_MINING");
-    if (env && atoi(env) != 0) return false;
+    return m_device_mining != 0 && !(env && atoi(env) != 0);
+}
+
+bool PatternManager::searchPatternDevice()
+{
+    if (!deviceMiningWanted()) return false;
     hmc_ctx *c = nullptr;
     try { c = m_builder.ctx(); }
     catch (const HmcError &) { if (m_device_mining > 0) throw; return false; }
@@ -452,7 +458,9 @@ bool PatternManager::searchPatternDevice()
     const int n = (int) sm.w.size();
     int64_t P = 0, na = 0;
     const double t0 = now_s();
-    int rc = hmc_mine_patterns(c, n, n ? sm.h.data() : nullptr, n ? sm.w.data() : nullptr, sm.total_weight, m_min_freq, m_min_len.data(), m_max_len.data(), &P, &na);
+    int rc = sm.on_device()
+        ? hmc_mine_patterns_resolved(c, n, sm.rows.data(), sm.w.data(), sm.total_weight, m_min_freq, m_min_len.data(), m_max_len.data(), &P, &na)
+        : hmc_mine_patterns(c, n, n ? sm.h.data() : nullptr, n ? sm.w.data() : nullptr, sm.total_weight, m_min_freq, m_min_len.data(), m_max_len.data(), &P, &na);
     if (rc < 0) throw HmcError(std::string("hmc_mine_patterns: ") + hmc_last_error(c));
     const double t1 = now_s();
     const hmc_pattern_rec *recs = nullptr;
@@ -780,8 +788,23 @@ void HaploBuilder::resolveAll(int sample_size, ResolveResult &r, bool want_haps)
     if (count == N) r.ll = ll_shard;
 }
 
+void HaploBuilder::materializeSamples()
+{
+    if (!m_samples.on_device()) return;
+    const int N = m_genos->N, L = m_genos->L;
+    std::vector<int8_t> all;
+    int rk = 0;
+    ck(m_ctx, hmc_result_dims(m_ctx, nullptr, &rk), "hmc_result_dims");
+    all.resize((size_t) N * rk * 2 * L);
+    ck(m_ctx, hmc_fetch_results(m_ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, all.data(), nullptr), "hmc_fetch_results");
+    m_samples.h.resize(m_samples.rows.size() * (size_t) L);
+    for (size_t s = 0; s < m_samples.rows.size(); ++s) memcpy(&m_samples.h[s * L], &all[(size_t) m_samples.rows[s] * L], (size_t) L);
+    m_samples.rows.clear();
+}
+
 void HaploBuilder::estimateFrequency(PatternSet &patterns)
 {
+    materializeSamples();       // the E-pass reuses the device result block the sample rows point into
     uploadModel();
     const int Pc = (int) patterns.size(), N = m_genos->N;
     std::vector<int32_t> start(Pc);
@@ -844,7 +867,16 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
     const int N = g.N, L = g.L;
     ResolveResult r;
     double t0 = now_s();
-    HaploBuilder::resolveAll(sample_size, r, true);
+    // One GPU holds every individual and the next search runs on it: the K sampled pairs stay on the device and are named by
+    // their result rows (hmc_mine_patterns_resolved); only the best pair of every individual comes back.
+    const bool dev_samples = m_patterns.deviceMiningWanted() && num_patterns <= 0 && !exact_estimate && (m_shard_count < 0 || m_shard_count == N) &&
+                             !getenv("HMC_B200_HOST_SAMPLES");
+    HaploBuilder::resolveAll(sample_size, r, !dev_samples);
+    std::vector<int8_t> best;
+    if (dev_samples) {
+        best.resize((size_t) N * 2 * L);
+        ck(m_ctx, hmc_fetch_best_haps(m_ctx, best.data()), "hmc_fetch_best_haps");
+    }
     seconds[1] += now_s() - t0;
     t0 = now_s();
     const int K = r.K;
@@ -858,11 +890,14 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
             memcpy(&resolved[(size_t) i * 2 * L], &g.idx[(size_t) i * 2 * L], (size_t) 2 * L);
         }
         else {
-            memcpy(&resolved[(size_t) i * 2 * L], &r.haps[((size_t) i * K) * 2 * L], (size_t) 2 * L);
+            memcpy(&resolved[(size_t) i * 2 * L], dev_samples ? &best[(size_t) i * 2 * L] : &r.haps[((size_t) i * K) * 2 * L], (size_t) 2 * L);
             for (int j = 0; j < n; ++j) {
                 const double wgt = r.posterior[(size_t) i * K + j] / r.coverage[i];
-                const int8_t *h = &r.haps[((size_t) i * K + j) * 2 * L];
-                m_samples.h.insert(m_samples.h.end(), h, h + 2 * L);
+                if (dev_samples) { m_samples.rows.push_back((i * K + j) * 2); m_samples.rows.push_back((i * K + j) * 2 + 1); }
+                else {
+                    const int8_t *h = &r.haps[((size_t) i * K + j) * 2 * L];
+                    m_samples.h.insert(m_samples.h.end(), h, h + 2 * L);
+                }
                 m_samples.w.push_back(wgt);
                 m_samples.w.push_back(wgt);
             }

@@ -74,11 +74,13 @@ struct PatternSet {
 // Weighted sampled haplotypes (HaploData as used by the sampling M-step, HaploModel.cpp:94-108)
 struct HaploData {
     int L = 0;
-    std::vector<int8_t> h;      // [n][L]
+    std::vector<int8_t> h;      // [n][L]; empty while the haplotypes are only on the device (`rows` names them)
     std::vector<double> w;
+    std::vector<int32_t> rows;  // device-resident samples: row of each haplotype in the result block of the last resolve pass
     double total_weight = 0;
     bool empty() const { return w.empty(); }
-    void clear() { h.clear(); w.clear(); total_weight = 0; }
+    bool on_device() const { return !rows.empty() && h.empty(); }
+    void clear() { h.clear(); w.clear(); rows.clear(); total_weight = 0; }
 };
 
 class HaploBuilder;
@@ -109,6 +111,7 @@ public:
     double min_freq() const { return m_min_freq; }
     void setThreads(int t) { m_threads = t; }
     void setDeviceMining(int mode) { m_device_mining = mode; }
+    bool deviceMiningWanted() const;    // device mining enabled and not overridden by HMC_B200_HOST_MINING
     double last_mine_seconds = 0;       // wall time of the last searchPattern
     bool last_mine_on_device = false;
 
@@ -180,6 +183,8 @@ public:
     };
     // resolve() of every individual in one call (HaploModel::resolveAll drives this)
     void resolveAll(int sample_size, ResolveResult &out, bool want_haps = true);
+    // device-resident samples -> host copies (only the host miner needs them)
+    void materializeSamples();
     // HaploBuilder::estimateFrequency(vector<HaploPattern*>&): fills frequency / prefix_freq / transition_prob
     void estimateFrequency(PatternSet &patterns);
     std::vector<int32_t> pg_exp;                // exponents carried next to genos()->genotype_probability (scaled mode)

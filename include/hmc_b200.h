@@ -132,6 +132,15 @@ int hmc_mine_patterns(hmc_ctx *ctx, int n_samples, const int8_t *sample_haps, co
                       double min_freq, const int32_t *min_len, const int32_t *max_len, int64_t *out_P, int64_t *out_n_alleles);
 int hmc_fetch_patterns(hmc_ctx *ctx, int32_t *start, int32_t *end, double *freq, double *prefix_freq, double *tp, int64_t *al_off,
                        int8_t *alleles);
+/* Sampling branch without moving the sampled haplotypes: rows [n_samples] index the haplotype rows
+ * ((individual - first) * K + k) * 2 + h that the last hmc_resolve_all / hmc_resolve_all_device call left on the device
+ * (HaploModel::resolveAll fills HaploData from exactly these rows, HaploModel.cpp:94-108). */
+int hmc_mine_patterns_resolved(hmc_ctx *ctx, int n_samples, const int32_t *rows, const double *sample_weights, double total_weight,
+                               double min_freq, const int32_t *min_len, const int32_t *max_len, int64_t *out_P, int64_t *out_n_alleles);
+/* Individuals and K of the result block the last resolve call left on the device (either pointer may be NULL). */
+int hmc_result_dims(hmc_ctx *ctx, int32_t *count, int32_t *K);
+/* The best resolution (k = 0) of every individual of the last resolve call: out_best [count][2][L]. */
+int hmc_fetch_best_haps(hmc_ctx *ctx, int8_t *out_best);
 /* The same list as records in page-locked host memory owned by the context (one D2H copy at link speed, no caller
  * buffers): valid until the next hmc_mine_patterns / hmc_ctx_destroy.  `al` is the offset of the allele string. */
 typedef struct hmc_pattern_rec {

@@ -119,3 +119,21 @@ def test_direct_abi_call_with_samples():
     st = dev.mine_stats()
     assert st["nodes"] >= r["P"] and st["levels"] >= 2
     dev.close()
+
+
+def test_device_resident_samples_equal_host_samples(monkeypatch):
+    """The sampled haplotypes normally stay on the device between the resolve pass and the next search
+    (hmc_mine_patterns_resolved); HMC_B200_HOST_SAMPLES=1 moves them through HaploData on the host as the reference does."""
+    out = []
+    for host_samples in (False, True):
+        if host_samples:
+            monkeypatch.setenv("HMC_B200_HOST_SAMPLES", "1")
+        hm = HaploModel(**{**model_opts("g4_em"), "max_iteration": 4, "device_mining": 1})
+        hm.load_phase(os.path.join(GOLDEN, "g4_em.phase"))
+        ll, npat = hm.run()
+        out.append((ll, npat, hm.resolutions(), hm.export_model()))
+        hm.close()
+    (l0, n0, r0, m0), (l1, n1, r1, m1) = out
+    assert len(l0) > 1 and np.array_equal(l0, l1) and np.array_equal(n0, n1) and np.array_equal(r0, r1)
+    for k in KEYS:
+        assert np.array_equal(m0[k], m1[k]), k
