@@ -17,6 +17,7 @@
 #include "forward_flat.cuh"
 #include "mine.cuh"
 #include "automaton.cuh"
+#include "compare.cuh"
 #include <cub/cub.cuh>
 #include "traceback.cuh"
 #include "estep.cuh"
@@ -74,6 +75,8 @@ struct hmc_ctx {
     int panel_serial = 0;           // bumped by every hmc_set_panel
     struct MinePool *mine = nullptr;
     struct AutPool *aut = nullptr;
+    DevBuf<signed char> d_cmp_real, d_cmp_infer;
+    DevBuf<CompareOut> d_cmp_out;
     DevBuf<signed char> d_raw;      // staging of the unpacked genotypes (kept: cudaMalloc/cudaFree per call cost 100s of ms)
     DevBuf<int> d_order;
     std::vector<int> h_order, h_rank;
@@ -489,7 +492,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     if (ctx->flat) { ctx->flat->release(); delete ctx->flat; }
     if (ctx->mine) { ctx->mine->release(); delete ctx->mine; }
     if (ctx->aut) { ctx->aut->release(); delete ctx->aut; }
-    ctx->d_af.release();
+    ctx->d_af.release(); ctx->d_cmp_real.release(); ctx->d_cmp_infer.release(); ctx->d_cmp_out.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -797,6 +800,41 @@ int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels
     if (max_list) *max_list = ctx->mine->max_list;
     if (swept) *swept = ctx->mine->swept;
     if (written) *written = ctx->mine->written;
+    return HMC_OK;
+}
+
+int hmc_compare(hmc_ctx *ctx, int N, int L, const int8_t *real, const int8_t *infer, int64_t out[6], int32_t *bad_individual, int32_t *bad_locus)
+{
+    if (!ctx || !real || !out || N <= 0 || L <= 0) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_compare: bad argument") : HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t bytes = (size_t) N * 2 * L;
+    CK(ctx->d_cmp_real.ensure(bytes)); CK(ctx->d_cmp_out.ensure(1));
+    CK(cudaMemcpyAsync(ctx->d_cmp_real.p, real, bytes, cudaMemcpyHostToDevice, st));
+    const signed char *inf = nullptr;
+    long long inf_stride = 2;
+    if (infer) {
+        CK(ctx->d_cmp_infer.ensure(bytes));
+        CK(cudaMemcpyAsync(ctx->d_cmp_infer.p, infer, bytes, cudaMemcpyHostToDevice, st));
+        inf = ctx->d_cmp_infer.p;
+    }
+    else {      // the best resolutions of the last resolve call, where they lie: row (i * K + 0) * 2 + h
+        if (ctx->r_count != N || ctx->L != L || !ctx->d_haps.p) return ctx->fail(HMC_ERR_INVALID, "hmc_compare: no resolve results for %d x %d on the device", N, L);
+        inf = ctx->d_haps.p; inf_stride = 2ll * ctx->r_K;
+    }
+    CompareOut h = {};
+    h.bad = ~0ull;
+    CK(cudaMemcpyAsync(ctx->d_cmp_out.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned) std::min<long long>(((long long) N * 32 + 255) / 256, (long long) ctx->sms * 16);
+    compare_kernel<<<grid, 256, 0, st>>>(ctx->d_cmp_real.p, 2, inf, inf_stride, N, L, ctx->d_cmp_out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h, ctx->d_cmp_out.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out[0] = h.se_num; out[1] = h.se_den; out[2] = h.ig_num; out[3] = h.ig_den; out[4] = h.ih_num; out[5] = h.ih_den;
+    const int bi = h.bad == ~0ull ? -1 : (int) (h.bad >> 32), bl = h.bad == ~0ull ? -1 : (int) (h.bad & 0xFFFFFFFFu);
+    if (bad_individual) *bad_individual = bi;
+    if (bad_locus) *bad_locus = bl;
+    if (bi >= 0) return ctx->fail(HMC_ERR_INVALID, "Inconsistent genotypes at locus %d! (individual %d)", bl, bi);
     return HMC_OK;
 }
 

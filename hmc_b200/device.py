@@ -21,7 +21,7 @@ CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps"
 EXPORTS = [
     "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",
     "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
-    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims",
+    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims", "hmc_compare",
     "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats",
 ]
 
@@ -60,6 +60,7 @@ def lib():
         L.hmc_build_automaton.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
         L.hmc_fetch_automaton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hmc_get_mine_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_int64)] * 5
+        L.hmc_compare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.hmc_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_trellis.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
@@ -206,6 +207,23 @@ class DeviceBuilder:
         heads = np.zeros(max(n_heads, 1), np.int32)
         self._ck(lib().hmc_fetch_automaton(self._h, _p(succ), _p(heads)))
         return dict(succ=succ, heads=heads[:n_heads])
+
+    def compare(self, real: np.ndarray, infer: np.ndarray | None = None) -> dict:
+        """HaploComp of `infer` (None = the best resolutions of the last resolve call, on the device) against `real`."""
+        real = np.ascontiguousarray(real, np.int8)
+        n, _, l = real.shape
+        if infer is not None:
+            infer = np.ascontiguousarray(infer, np.int8)
+            assert infer.shape == real.shape
+        out = np.zeros(6, np.int64)
+        bi, bl = C.c_int32(-1), C.c_int32(-1)
+        rc = lib().hmc_compare(self._h, n, l, _p(real), _p(infer), _p(out), C.byref(bi), C.byref(bl))
+        if rc < 0 and bi.value < 0:
+            self._ck(rc)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f = out.astype(np.float64)
+            return dict(counts=out, switch_error=float(f[0] / f[1]), igp=float(f[2] / f[3]), ihp=float(f[4] / f[5]), bad_individual=bi.value,
+                        bad_locus=bl.value)
 
     def mine_stats(self) -> dict:
         ms, nodes, levels, mx, sw, wr = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

@@ -35,6 +35,7 @@ static void usage()
            "  -i [ --max-iteration ] arg (=1)  Maximum iteration number\n"
            "  --min-iteration arg (=-1)     Minimum iteration number (accepted, unused)\n"
            "Device options (new):\n"
+           "  -e [ --compare ]              Compare input data with target data: hmc -e INFERRED.phase TARGET.phase\n"
            "  --device arg (=0)             CUDA device\n"
            "  --scaled                      carry a power-of-two exponent so that long panels do not underflow\n"
            "  --threads arg (=0)            threads per individual on the device (0 = auto)\n");
@@ -43,7 +44,8 @@ static void usage()
 int main(int argc, char **argv)
 {
     try {
-        std::string model = "MV", input, format = "PHASE";
+        std::string model = "MV", input, target, format = "PHASE";
+        bool compare = false;
         int device = 0, debug = 4, threads = 0;
         bool nologo = false, scaled = false;
         // first pass for device options
@@ -78,8 +80,10 @@ int main(int argc, char **argv)
             else if (a == "--min-iteration") hm.min_iteration = atoi(next().c_str());
             else if (a == "--device" || a == "--threads") next();
             else if (a == "--scaled") scaled = true;
+            else if (a == "-e" || a == "--compare") compare = true;
             else if (!a.empty() && a[0] == '-') throw HmcError("unknown option " + a);
-            else input = a;
+            else if (input.empty()) input = a;
+            else target = a;
         }
         if (format != "PHASE") throw HmcError("Unknown input format " + format + "! (this build reads PHASE files)");
         if (input.empty()) { usage(); return 0; }
@@ -94,6 +98,15 @@ int main(int argc, char **argv)
         if (debug >= 3) printf("Reading genotype file ...\n");
         file.readGenoData(genos);
         if (debug >= 3) printf("Succesfully read Haplotype file with %d markers and %d genotypes.\n", genos.L, genos.N);
+        if (compare) {       // HMC::compare (HMC.cpp:246-257): the first file is the inferred data, the second the target
+            if (target.empty()) throw HmcError("Input format " + format + " require 1 filenames! (--compare needs INPUT and TARGET)");
+            GenoData tg;
+            HaploFile(target).readGenoData(tg);
+            if (debug >= 3) printf("Succesfully read Haplotype file with %d markers and %d genotypes.\n", tg.L, tg.N);
+            HaploComp hc(hm, tg, genos);
+            printf("\nSwitch Error = %f, IHP = %f, IGP = %f\n", hc.switch_error(), hc.incorrect_haplotype_percentage(), hc.incorrect_genotype_percentage());
+            return 0;
+        }
         std::vector<int8_t> resolutions;
         hm.run(genos, resolutions);
         if (debug >= 3) {

@@ -911,6 +911,37 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
     return r.ll;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HaploComp
+HaploComp::HaploComp(HaploBuilder &hb, int N, int L, const int8_t *real, const int8_t *infer)
+{
+    hmc_ctx *c = hb.ctx();
+    int32_t bi = -1, bl = -1;
+    if (hmc_compare(c, N, L, real, infer, counts, &bi, &bl) < 0) throw HmcError(hmc_last_error(c));
+}
+
+HaploComp::HaploComp(HaploBuilder &hb, const GenoData &real, const GenoData &infer)
+{
+    if (real.N != infer.N || real.L != infer.L) throw HmcError("Attempt to compare inconsistent haplotype data!");      // HaploComp.cpp:36-40
+    const int N = real.N, L = real.L;
+    std::vector<int8_t> a((size_t) N * 2 * L), b((size_t) N * 2 * L);
+    for (int l = 0; l < L; ++l) {
+        std::vector<int32_t> u(real.symbols[l]);
+        u.insert(u.end(), infer.symbols[l].begin(), infer.symbols[l].end());
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        if (u.size() > 127) throw HmcError("too many distinct alleles at locus " + std::to_string(l));
+        auto code = [&](int v) { return v < 0 ? -1 : (int) (std::lower_bound(u.begin(), u.end(), v) - u.begin()); };
+        for (int i = 0; i < N; ++i) for (int h = 0; h < 2; ++h) {
+            a[((size_t) i * 2 + h) * L + l] = (int8_t) code(real.allele(i, h, l));
+            b[((size_t) i * 2 + h) * L + l] = (int8_t) code(infer.allele(i, h, l));
+        }
+    }
+    hmc_ctx *c = hb.ctx();
+    int32_t bi = -1, bl = -1;
+    if (hmc_compare(c, N, L, a.data(), b.data(), counts, &bi, &bl) < 0) throw HmcError(hmc_last_error(c));
+}
+
 void HaploModel::run(const GenoData &genos, std::vector<int8_t> &resolutions)
 {
     m_unphased = genos;
@@ -924,7 +955,11 @@ void HaploModel::run(const GenoData &genos, std::vector<int8_t> &resolutions)
         const double ll = resolveAll(resolved);
         ll_trace.push_back(ll);
         if (ll >= old_ll) resolutions = resolved;
-        if (verbose) fprintf(stderr, "  iteration %d: patterns %d, LL = %f\n", iter, m_patterns.size(), ll);
+        if (verbose) {      // HaploModel.cpp:134-137
+            HaploComp compare(*this, m_unphased.N, m_unphased.L, m_unphased.idx.data(), resolutions.data());
+            fprintf(stderr, "  iteration %d: patterns %d, Switch Error = %f, IHP = %f, IGP = %f, LL = %f\n", iter, m_patterns.size(), compare.switch_error(),
+                    compare.incorrect_haplotype_percentage(), compare.incorrect_genotype_percentage(), ll);
+        }
         if (iter < max_iteration && ll >= old_ll && (old_ll - ll) / old_ll > 0.0001) {
             if (exact_estimate) { const double t0 = now_s(); m_patterns.estimatePatterns(); seconds[2] += now_s() - t0; }
             else findPatterns();

@@ -190,6 +190,20 @@ public:
     std::vector<int32_t> pg_exp;                // exponents carried next to genos()->genotype_probability (scaled mode)
 };
 
+// HaploComp (HaploComp.h:10-45, HaploComp.cpp:29-76) on the device (K7): switch error, incorrect-haplotype and
+// incorrect-genotype percentages of `infer` against `real`.
+struct HaploComp {
+    int64_t counts[6] = {0, 0, 0, 0, 0, 0};     // numerators / denominators in the order SE, IGP, IHP
+    double switch_error() const { return (double) counts[0] / counts[1]; }
+    double incorrect_genotype_percentage() const { return (double) counts[2] / counts[3]; }
+    double incorrect_haplotype_percentage() const { return (double) counts[4] / counts[5]; }
+    // both sides as allele INDICES of the same panel ([N][2][L], -1 missing); infer == nullptr: the best resolutions of the
+    // last resolve pass, compared where they lie in device memory
+    HaploComp(HaploBuilder &hb, int N, int L, const int8_t *real, const int8_t *infer);
+    // two panels with their own symbol tables (HMC::compare, HMC.cpp:246-257): a joint per-locus coding is built first
+    HaploComp(HaploBuilder &hb, const GenoData &real, const GenoData &infer);
+};
+
 // HaploModel (HaploModel.h:10-40): option fields + EM driver.
 class HaploModel : public HaploBuilder {
 protected:

@@ -159,6 +159,14 @@ int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads);
  * swept / written: match-list entries read by the sweeps / written into child lists (the roofline's traffic model). */
 int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels, int64_t *max_list, int64_t *swept, int64_t *written);
 
+/* K7: HaploComp (HaploComp.cpp:29-76, as used by HaploModel::run :134 and HMC::compare, HMC.cpp:246-257) of inferred
+ * against real (target) phased genotypes, both [N][2][L] allele codes in any per-locus coding shared by the two sides
+ * (negative = missing).  infer == NULL compares the best resolutions of the last resolve call where they lie on the device.
+ * out: switch-error numerator / denominator, incorrect-genotype num / den, incorrect-haplotype num / den; the three ratios
+ * are num / den in double (HaploComp.cpp:145-147).  Data the reference would exit on ("Inconsistent genotypes at locus
+ * %d!", Genotype.cpp:258-261,272-275) returns HMC_ERR_INVALID with the first offending individual / locus. */
+int hmc_compare(hmc_ctx *ctx, int N, int L, const int8_t *real, const int8_t *infer, int64_t out[6], int32_t *bad_individual, int32_t *bad_locus);
+
 /* Structural counters of the last resolve/estimate call (HMC_CNT_*), for parity and the roofline. */
 int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N]);
 /* Device time (ms, CUDA events) of the kernels of the last call: [0] forward, [1] traceback, [2] backward, [3] E-step. */

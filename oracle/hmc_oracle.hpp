@@ -920,4 +920,52 @@ struct HaploModel {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// HaploComp (HaploComp.cpp:29-76) over allele codes (any per-locus coding shared by both sides, negative = missing):
+// real = the target / true data, infer = the resolutions.  Alleles "match" when either is missing (Allele.h:20).
+struct CompareResult {
+    long long se_num = 0, se_den = 0, ig_num = 0, ig_den = 0, ih_num = 0, ih_den = 0;
+    int bad_individual = -1, bad_locus = -1;        // "Inconsistent genotypes at locus %d!" (Genotype.cpp:258-261,272-275): the reference exits
+    double switch_error() const { return (double) se_num / se_den; }                       // HaploComp.cpp:145-147 (0/0 is NaN there too)
+    double incorrect_genotype_percentage() const { return (double) ig_num / ig_den; }
+    double incorrect_haplotype_percentage() const { return (double) ih_num / ih_den; }
+};
+
+inline CompareResult compare_genotypes(const int8_t *real, const int8_t *infer, int N, int L)
+{
+    CompareResult r;
+    auto am = [](int a, int b) { return a < 0 || b < 0 || a == b; };       // Allele::isMatch
+    for (int i = 0; i < N; ++i) {
+        const int8_t *r0 = real + ((size_t) i * 2) * L, *r1 = r0 + L, *f0 = infer + ((size_t) i * 2) * L, *f1 = f0 + L;
+        auto match = [&](int l, bool rev) { return rev ? (am(r0[l], f1[l]) && am(r1[l], f0[l])) : (am(r0[l], f0[l]) && am(r1[l], f1[l])); };   // Genotype.cpp:98-118
+        auto has_missing = [&](int l) { return r0[l] < 0 || r1[l] < 0; };  // Genotype.h:120-123
+        int het = 0, miss = 0;                                              // Genotype::checkGenotype, Genotype.cpp:44-56
+        for (int l = 0; l < L; ++l) { if (!am(r0[l], r1[l])) ++het; if (has_missing(l)) ++miss; }
+        // getSwitchDistanceIgnoreMissing, Genotype.cpp:235-279
+        int sd = 0, start = L;
+        for (int l = 0; l < L; ++l) { if (has_missing(l) || (match(l, true) && match(l, false))) continue; start = l; break; }
+        if (start < L) {
+            bool reversed;
+            if (match(start, true)) reversed = true;
+            else if (match(start, false)) reversed = false;
+            else { if (r.bad_individual < 0) { r.bad_individual = i; r.bad_locus = start; } continue; }
+            bool bad = false;
+            for (int l = start + 1; l < L; ++l) {
+                if (has_missing(l) || match(l, reversed)) continue;
+                if (match(l, !reversed)) { reversed = !reversed; ++sd; }
+                else { if (r.bad_individual < 0) { r.bad_individual = i; r.bad_locus = l; } bad = true; break; }
+            }
+            if (bad) continue;
+        }
+        // getDiffNumIgnoreMissing, Genotype.cpp:160-175
+        int d1 = 0, d2 = 0;
+        for (int l = 0; l < L; ++l) if (!has_missing(l)) { if (!match(l, true)) ++d1; if (!match(l, false)) ++d2; }
+        r.se_num += sd; r.se_den += het - 1;                                // HaploComp.cpp:58-61
+        r.ig_num += d1 < d2 ? d1 : d2; r.ig_den += L - miss;                // :62-65
+        if (sd > 0) ++r.ih_num;                                             // :66-68
+        if (het > 1) ++r.ih_den;
+    }
+    return r;
+}
+
 }  // namespace orc

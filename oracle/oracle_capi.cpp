@@ -177,6 +177,15 @@ void orc_get_trace(void *p, double *ll, int *npat)
     Handle *h = (Handle *) p;
     for (size_t i = 0; i < h->hm.ll_trace.size(); ++i) { ll[i] = h->hm.ll_trace[i]; npat[i] = h->hm.npat_trace[i]; }
 }
+// HaploComp over allele codes [N][2][L]; out6 = se_num, se_den, ig_num, ig_den, ih_num, ih_den; returns the first inconsistent individual or -1
+int orc_compare(const int8_t *real, const int8_t *infer, int N, int L, long long *out6, int *bad_locus)
+{
+    const orc::CompareResult r = orc::compare_genotypes(real, infer, N, L);
+    out6[0] = r.se_num; out6[1] = r.se_den; out6[2] = r.ig_num; out6[3] = r.ig_den; out6[4] = r.ih_num; out6[5] = r.ih_den;
+    if (bad_locus) *bad_locus = r.bad_locus;
+    return r.bad_individual;
+}
+
 double orc_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // extern "C"

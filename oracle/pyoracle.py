@@ -154,3 +154,19 @@ class Oracle:
         npat = np.zeros(n, np.int32)
         lib().orc_get_trace(self._h, _p(ll), _p(npat))
         return ll, npat
+
+
+def compare(real: np.ndarray, infer: np.ndarray) -> dict:
+    """HaploComp (HaploComp.cpp:29-76) over allele codes [N][2][L] (negative = missing): counters and the three ratios."""
+    real = np.ascontiguousarray(real, np.int8)
+    infer = np.ascontiguousarray(infer, np.int8)
+    assert real.shape == infer.shape and real.ndim == 3 and real.shape[1] == 2
+    out = np.zeros(6, np.int64)
+    bad_locus = C.c_int(-1)
+    L_ = lib()
+    L_.orc_compare.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    bad = L_.orc_compare(_p(real), _p(infer), real.shape[0], real.shape[2], _p(out), C.byref(bad_locus))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = out.astype(np.float64)
+        return dict(counts=out, switch_error=float(f[0] / f[1]), igp=float(f[2] / f[3]), ihp=float(f[4] / f[5]), bad_individual=bad,
+                    bad_locus=bad_locus.value)

@@ -254,7 +254,8 @@ static void usage()
 		"    -a/--min-freq-abs 1.5, -n/--num-patterns n, --min-pattern-len 1, --max-pattern-len 30, -o/--mc-order 1,\n"
 		"    --exact-estimate, --sample-size 10, -i/--max-iteration 1, -d/--debug 2\n"
 		"  driver options: --dump FILE [--dump-states] [--dump-beta] [--dump-estep] [--no-patterns] [--no-klist]\n"
-		"    --out-suffix S (default .reconstructed; 'none' to skip), --time-resolve n [--time-estep m]\n");
+		"    --out-suffix S (default .reconstructed; 'none' to skip), --time-resolve n [--time-estep m]\n"
+		"    --compare REAL.phase: HaploComp of the positional (inferred) file against REAL, printed as hex floats\n");
 }
 
 int main(int argc, char **argv)
@@ -271,6 +272,7 @@ int main(int argc, char **argv)
 	m.max_iteration = 1;
 	m.min_iteration = -1;
 	int debug = 2;
+	string compare_with;
 	for (int i = 1; i < argc; ++i) {
 		string a = argv[i];
 		auto next = [&]() -> const char * { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
@@ -297,6 +299,7 @@ int main(int argc, char **argv)
 		else if (a == "--time-offset") m.opt.time_offset = atoi(next());
 		else if (a == "--time-steps") m.opt.time_steps = atoi(next());
 		else if (a == "--time-warmup") m.opt.time_warmup = atoi(next());
+		else if (a == "--compare") compare_with = next();
 		else if (a[0] == '-') { usage(); return 2; }
 		else m.opt.input = a;
 	}
@@ -308,6 +311,15 @@ int main(int argc, char **argv)
 	GenoData genos, resolutions;
 	file.readGenoData(genos);
 
+	if (!compare_with.empty()) {
+		// HMC::compare (HMC.cpp:246-257): the positional file is the inferred data, --compare names the real (target) data
+		GenoData target;
+		HaploFile(compare_with).readGenoData(target);
+		HaploComp hc(&target, &genos);
+		printf("{\"switch_error\": \"%a\", \"ihp\": \"%a\", \"igp\": \"%a\"}\n", hc.switch_error(), hc.incorrect_haplotype_percentage(),
+		       hc.incorrect_genotype_percentage());
+		return 0;
+	}
 	if (m.opt.time_resolve > 0) {
 		m.timeLegs(genos);
 		return 0;
