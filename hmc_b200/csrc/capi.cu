@@ -19,6 +19,7 @@
 #include "automaton.cuh"
 #include "compare.cuh"
 #include <cub/cub.cuh>
+#include <climits>
 #include "traceback.cuh"
 #include "estep.cuh"
 
@@ -89,6 +90,7 @@ struct hmc_ctx {
     DevBuf<int4> d_succ16;
     DevBuf<double> d_tp, d_freq;
     DevBuf<unsigned char> d_last;
+    DevBuf<int> d_end_tmp, d_model_err;
     DevBuf<long long> d_al_off;
     DevBuf<signed char> d_al;
 
@@ -155,13 +157,26 @@ __global__ void pack_kernel(const signed char *geno, int N, int L, int bits, int
     packed[t] = v;
 }
 
+// K0: per-pattern consistency checks of an uploaded model and the last allele of every pattern, one thread per pattern;
+// err[0] = smallest inconsistent pattern id (INT_MAX if none)
+__global__ void model_check_kernel(int P, int L, const int *start, const int *end, const long long *al_off, long long total, const signed char *al,
+                                   unsigned char *last, int *err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const long long a0 = al_off[i], a1 = al_off[i + 1];
+    const int s = start[i], e = end[i];
+    if (a0 < 0 || a1 > total || a1 - a0 != (long long) e - s || e <= s || e > L || s < 0) { atomicMin(err, i); return; }
+    last[i] = (unsigned char) al[a1 - 1];
+}
+
 // K0: successor table flattening, one thread per (pattern, allele)
-__global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P, int4 *out, int *)
+__global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P, int4 *out, int *err)
 {
     const size_t q = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (q >= n) return;
     int id = succ[q];
-    if (id >= P) id = -1;
+    if (id >= P || id < -1) { if (err) atomicMin(err + 1, (int) (q / (n / P))); id = -1; }
     const double t = id >= 0 ? tp[id] : 0.0;
     out[q] = make_int4(id, 0, __double2loint(t), __double2hiint(t));
 }
@@ -482,7 +497,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
-    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release();
+    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
     ctx->d_wave.release(); ctx->d_status.release(); ctx->d_final_exp.release(); ctx->d_locus_exp.release();
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
@@ -558,12 +573,9 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     if (head_len < 1 || head_len > 8 || head_len > ctx->L) return ctx->fail(HMC_ERR_LIMIT, "head length %d outside [1,8]", head_len);
     CK(cudaSetDevice(ctx->device));
     const int A = ctx->Amax;
-    std::vector<unsigned char> last(P);
-    for (int i = 0; i < P; ++i) {
-        if (al_off[i + 1] - al_off[i] != end[i] - start[i] || end[i] <= start[i] || end[i] > ctx->L || start[i] < 0)
-            return ctx->fail(HMC_ERR_INVALID, "pattern %d: inconsistent start/end/alleles", i);
-        last[i] = (unsigned char) alleles[al_off[i + 1] - 1];
-    }
+    // per-pattern checks, the last alleles and the successor range check run on the device after the upload (model_check_kernel,
+    // succ16_kernel): host loops over millions of patterns would cost more than the copies
+    if (al_off[0] != 0 || al_off[P] < P) return ctx->fail(HMC_ERR_INVALID, "pattern allele offsets are inconsistent");
     // head lookup: mixed-radix code over the first head_len loci, locus 0 most significant
     int stride[8] = {0};
     long long size = 1;
@@ -571,12 +583,12 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     std::vector<int> lut((size_t) size, -1);
     for (int h = 0; h < n_heads; ++h) {
         const int id = heads[h];
-        if (id < 0 || id >= P || start[id] != 0 || end[id] != head_len) return ctx->fail(HMC_ERR_INVALID, "head %d is not a start-0 pattern of length head_len", id);
+        if (id < 0 || id >= P || start[id] != 0 || end[id] != head_len || al_off[id] < 0 || al_off[id] + head_len > al_off[P])
+            return ctx->fail(HMC_ERR_INVALID, "head %d is not a start-0 pattern of length head_len", id);
         long long code = 0;
         for (int j = 0; j < head_len; ++j) code += (long long) alleles[al_off[id] + j] * stride[j];
         lut[(size_t) code] = id;
     }
-    for (size_t q = 0; q < (size_t) P * A; ++q) if (succ[q] >= P || succ[q] < -1) return ctx->fail(HMC_ERR_INVALID, "successor id out of range");
     CK(ctx->d_succ16.ensure((size_t) P * A));
     CK(ctx->d_succ.ensure((size_t) P * A)); CK(ctx->d_start.ensure(P)); CK(ctx->d_tp.ensure(P)); CK(ctx->d_freq.ensure(P)); CK(ctx->d_last.ensure(P));
     CK(ctx->d_al_off.ensure(P + 1)); CK(ctx->d_al.ensure((size_t) al_off[P] + 1)); CK(ctx->d_heads.ensure(std::max(1, n_heads))); CK(ctx->d_head_lut.ensure(lut.size()));
@@ -585,7 +597,10 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     CK(cudaMemcpyAsync(ctx->d_start.p, start, sizeof(int) * P, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_tp.p, tp, sizeof(double) * P, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_freq.p, freq, sizeof(double) * P, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_last.p, last.data(), P, cudaMemcpyHostToDevice, st));
+    CK(ctx->d_end_tmp.ensure(P)); CK(ctx->d_model_err.ensure(2));
+    CK(cudaMemcpyAsync(ctx->d_end_tmp.p, end, sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    const int err_init[2] = {INT_MAX, INT_MAX};
+    CK(cudaMemcpyAsync(ctx->d_model_err.p, err_init, sizeof err_init, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_al_off.p, al_off, sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_al.p, alleles, (size_t) al_off[P], cudaMemcpyHostToDevice, st));
     if (n_heads > 0) CK(cudaMemcpyAsync(ctx->d_heads.p, heads, sizeof(int) * n_heads, cudaMemcpyHostToDevice, st));
@@ -593,10 +608,19 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     // 16-byte successor entries {successor id, pad, transition_prob(successor)}: one 128-bit gather yields both (K0 flatten)
     {
         const size_t n = (size_t) P * A;
-        succ16_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(ctx->d_succ.p, ctx->d_tp.p, n, P, ctx->d_succ16.p, ctx->d_flags.p ? ctx->d_flags.p + 1 : nullptr);
+        model_check_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(P, ctx->L, ctx->d_start.p, ctx->d_end_tmp.p, ctx->d_al_off.p, (long long) al_off[P], ctx->d_al.p,
+                                                                         ctx->d_last.p, ctx->d_model_err.p);
+        succ16_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(ctx->d_succ.p, ctx->d_tp.p, n, P, ctx->d_succ16.p, ctx->d_model_err.p);
         CK(cudaGetLastError());
     }
+    int err[2] = {INT_MAX, INT_MAX};
+    CK(cudaMemcpyAsync(err, ctx->d_model_err.p, sizeof err, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (err[0] != INT_MAX || err[1] != INT_MAX) {
+        ctx->have_model = false;
+        if (err[0] != INT_MAX) return ctx->fail(HMC_ERR_INVALID, "pattern %d: inconsistent start/end/alleles", err[0]);
+        return ctx->fail(HMC_ERR_INVALID, "successor id out of range (pattern %d)", err[1]);
+    }
     DevModel &m = ctx->dm;
     m.P = P; m.head_len = head_len; m.n_heads = n_heads; m.Amax = A;
     m.succ = ctx->d_succ.p; m.succ16 = ctx->d_succ16.p; m.tp = ctx->d_tp.p; m.freq = ctx->d_freq.p; m.start = ctx->d_start.p; m.last = ctx->d_last.p;

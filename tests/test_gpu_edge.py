@@ -111,6 +111,13 @@ def test_misuse_is_an_error_code_not_a_crash():
     bad["succ"][0, 0] = m["P"] + 5
     with pytest.raises(HmcError):
         dev.set_model(bad)
+    with pytest.raises(HmcError):
+        dev.resolve_all(K=1)                        # a rejected model is not left installed
+    bad = dict(m)
+    bad["end"] = m["end"].copy()
+    bad["end"][m["P"] // 2] += 1                    # start/end no longer agree with the allele string
+    with pytest.raises(HmcError, match="inconsistent start/end/alleles"):
+        dev.set_model(bad)
     dev.set_model(m)
     r = dev.resolve_all(K=3, first=2, count=4)      # a sub-range works and is indexed from `first`
     o.set_options(sample_size=3)
