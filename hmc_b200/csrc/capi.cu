@@ -77,6 +77,7 @@ struct hmc_ctx {
     struct MinePool *mine = nullptr;
     struct AutPool *aut = nullptr;
     DevBuf<signed char> d_cmp_real, d_cmp_infer;
+    DevBuf<u32> d_best_packed;
     DevBuf<CompareOut> d_cmp_out;
     DevBuf<signed char> d_raw;      // staging of the unpacked genotypes (kept: cudaMalloc/cudaFree per call cost 100s of ms)
     DevBuf<int> d_order;
@@ -90,7 +91,7 @@ struct hmc_ctx {
     DevBuf<int4> d_succ16;
     DevBuf<double> d_tp, d_freq;
     DevBuf<unsigned char> d_last;
-    DevBuf<int> d_end_tmp, d_model_err;
+    DevBuf<int> d_end_tmp, d_model_err, d_miss;
     DevBuf<long long> d_al_off;
     DevBuf<signed char> d_al;
 
@@ -155,6 +156,46 @@ __global__ void pack_kernel(const signed char *geno, int N, int L, int bits, int
         }
     }
     packed[t] = v;
+}
+
+// the best resolution of every individual (row stride = K * 2 haplotype rows) in the packed panel layout
+__global__ void pack_strided_kernel(const signed char *haps, long long row_stride, int N, int L, int bits, int words, u32 *packed)
+{
+    const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (t >= (size_t) N * words) return;
+    const int ind = (int) (t / words), wd = (int) (t % words);
+    const int per = 32 / (2 * bits);
+    const signed char *g0 = haps + (size_t) ind * row_stride * L, *g1 = g0 + L;
+    u32 v = 0;
+    for (int q = 0; q < per; ++q) {
+        const int l = wd * per + q;
+        if (l < L) v |= ((u32) (g0[l] + 1) | ((u32) (g1[l] + 1) << bits)) << (q * 2 * bits);
+    }
+    packed[t] = v;
+}
+
+// K0 for panels that arrive bit-packed (binary panel files): the inverse of pack_kernel into the unpacked staging copy that the
+// miner and the comparison read, the missing-allele count per individual (work order) and a range check of the codes
+__global__ void unpack_kernel(const u32 *packed, int N, int L, int bits, int words, int Amax, signed char *geno, int *miss, int *err)
+{
+    const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (t >= (size_t) N * words) return;
+    const int ind = (int) (t / words), wd = (int) (t % words);
+    const int per = 32 / (2 * bits);
+    const u32 m = (1u << bits) - 1u;
+    signed char *g0 = geno + ((size_t) ind * 2) * L, *g1 = g0 + L;
+    const u32 v = packed[t];
+    int nm = 0;
+    for (int q = 0; q < per; ++q) {
+        const int l = wd * per + q;
+        if (l >= L) break;
+        const u32 c = v >> (q * 2 * bits);
+        const int a = (int) (c & m) - 1, b = (int) ((c >> bits) & m) - 1;
+        if (a >= Amax || b >= Amax) atomicMin(err, ind);
+        g0[l] = (signed char) a; g1[l] = (signed char) b;
+        nm += (a < 0) + (b < 0);
+    }
+    if (nm) atomicAdd(miss + ind, nm);
 }
 
 // K0: per-pattern consistency checks of an uploaded model and the last allele of every pattern, one thread per pattern;
@@ -497,7 +538,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
-    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release();
+    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release(); ctx->d_miss.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
     ctx->d_wave.release(); ctx->d_status.release(); ctx->d_final_exp.release(); ctx->d_locus_exp.release();
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
@@ -507,7 +548,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     if (ctx->flat) { ctx->flat->release(); delete ctx->flat; }
     if (ctx->mine) { ctx->mine->release(); delete ctx->mine; }
     if (ctx->aut) { ctx->aut->release(); delete ctx->aut; }
-    ctx->d_af.release(); ctx->d_cmp_real.release(); ctx->d_cmp_infer.release(); ctx->d_cmp_out.release();
+    ctx->d_af.release(); ctx->d_best_packed.release(); ctx->d_cmp_real.release(); ctx->d_cmp_infer.release(); ctx->d_cmp_out.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -562,6 +603,50 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     pack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, ctx->stream>>>(raw.p, N, L, ctx->bits, ctx->words, ctx->d_packed.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    return HMC_OK;
+}
+
+int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const uint32_t *packed, const int32_t *n_alleles, const double *allele_freq)
+{
+    if (!ctx || N <= 0 || L <= 0 || !packed || !n_alleles || !allele_freq) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_set_panel_packed: bad argument") : HMC_ERR_INVALID;
+    if (Amax < 1 || Amax > HMC_MAX_ALLELES) return ctx->fail(HMC_ERR_LIMIT, "Amax %d outside [1,%d]", Amax, HMC_MAX_ALLELES);
+    if (bits != (Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8))) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel_packed: %d bits per allele do not match Amax %d", bits, Amax);
+    CK(cudaSetDevice(ctx->device));
+    ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
+    const int per = 32 / (2 * bits);
+    ctx->words = (L + per - 1) / per;
+    std::vector<u32> amask(L, 0);
+    ctx->h_nall.assign(n_alleles, n_alleles + L);
+    for (int l = 0; l < L; ++l) {
+        if (n_alleles[l] < 0 || n_alleles[l] > Amax) return ctx->fail(HMC_ERR_INVALID, "n_alleles[%d] = %d outside [0,%d]", l, n_alleles[l], Amax);
+        for (int j = 0; j < n_alleles[l]; ++j) if (allele_freq[(size_t) l * Amax + j] > 0) amask[l] |= 1u << j;
+        amask[l] = (u32) n_alleles[l] | (amask[l] << 8);
+    }
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_packed.ensure((size_t) N * ctx->words)); CK(ctx->d_linfo.ensure(L)); CK(ctx->d_order.ensure(N)); CK(ctx->d_raw.ensure((size_t) N * 2 * L));
+    CK(ctx->d_af.ensure((size_t) L * Amax)); CK(ctx->d_miss.ensure((size_t) N + 1));
+    CK(cudaMemcpyAsync(ctx->d_packed.p, packed, sizeof(u32) * (size_t) N * ctx->words, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_linfo.p, amask.data(), sizeof(u32) * L, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_af.p, allele_freq, sizeof(double) * (size_t) L * Amax, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_miss.p, 0, sizeof(int) * N, st));
+    const int big = INT_MAX;
+    CK(cudaMemcpyAsync(ctx->d_miss.p + N, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+    const size_t nthr = (size_t) N * ctx->words;
+    unpack_kernel<<<(unsigned) ((nthr + 255) / 256), 256, 0, st>>>(ctx->d_packed.p, N, L, bits, ctx->words, Amax, ctx->d_raw.p, ctx->d_miss.p, ctx->d_miss.p + N);
+    CK(cudaGetLastError());
+    std::vector<int> miss((size_t) N + 1);
+    CK(cudaMemcpyAsync(miss.data(), ctx->d_miss.p, sizeof(int) * ((size_t) N + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (miss[N] != INT_MAX) return ctx->fail(HMC_ERR_INVALID, "allele index out of range at individual %d", miss[N]);
+    size_t tot_miss = 0;
+    for (int i = 0; i < N; ++i) tot_miss += miss[i];
+    ctx->missing_frac = (double) tot_miss / ((double) N * L * 2);
+    ctx->h_order.resize(N);
+    for (int i = 0; i < N; ++i) ctx->h_order[i] = i;
+    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) { return miss[a] > miss[b]; });
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    ++ctx->panel_serial;
     return HMC_OK;
 }
 
@@ -747,6 +832,20 @@ int hmc_fetch_best_haps(hmc_ctx *ctx, int8_t *out_best)
     CK(cudaSetDevice(ctx->device));
     const size_t row = (size_t) 2 * ctx->L;
     CK(cudaMemcpy2DAsync(out_best, row, ctx->d_haps.p, row * ctx->r_K, row, ctx->r_count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HMC_OK;
+}
+
+int hmc_fetch_best_packed(hmc_ctx *ctx, uint32_t *out_packed)
+{
+    if (!ctx || !out_packed || ctx->r_count <= 0) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_fetch_best_packed: no results to fetch") : HMC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t) ctx->r_count * ctx->words;
+    CK(ctx->d_best_packed.ensure(n));
+    pack_strided_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_haps.p, (long long) ctx->r_K * 2, ctx->r_count, ctx->L, ctx->bits, ctx->words,
+                                                                              ctx->d_best_packed.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_packed, ctx->d_best_packed.p, sizeof(u32) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return HMC_OK;
 }

@@ -21,7 +21,7 @@ CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps"
 EXPORTS = [
     "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",
     "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
-    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims", "hmc_compare",
+    "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims", "hmc_compare", "hmc_set_panel_packed", "hmc_fetch_best_packed",
     "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats",
 ]
 

@@ -35,6 +35,7 @@ static void usage()
            "  -i [ --max-iteration ] arg (=1)  Maximum iteration number\n"
            "  --min-iteration arg (=-1)     Minimum iteration number (accepted, unused)\n"
            "Device options (new):\n"
+           "  --to-binary arg               Convert the input panel to the bit-packed binary format (HMCB) and exit\n"
            "  -e [ --compare ]              Compare input data with target data: hmc -e INFERRED.phase TARGET.phase\n"
            "  --device arg (=0)             CUDA device\n"
            "  --scaled                      carry a power-of-two exponent so that long panels do not underflow\n"
@@ -44,7 +45,7 @@ static void usage()
 int main(int argc, char **argv)
 {
     try {
-        std::string model = "MV", input, target, format = "PHASE";
+        std::string model = "MV", input, target, to_binary, format = "PHASE";
         bool compare = false;
         int device = 0, debug = 4, threads = 0;
         bool nologo = false, scaled = false;
@@ -81,6 +82,7 @@ int main(int argc, char **argv)
             else if (a == "--device" || a == "--threads") next();
             else if (a == "--scaled") scaled = true;
             else if (a == "-e" || a == "--compare") compare = true;
+            else if (a == "--to-binary") to_binary = next();
             else if (!a.empty() && a[0] == '-') throw HmcError("unknown option " + a);
             else if (input.empty()) input = a;
             else target = a;
@@ -98,6 +100,11 @@ int main(int argc, char **argv)
         if (debug >= 3) printf("Reading genotype file ...\n");
         file.readGenoData(genos);
         if (debug >= 3) printf("Succesfully read Haplotype file with %d markers and %d genotypes.\n", genos.L, genos.N);
+        if (!to_binary.empty()) {   // PHASE text -> binary panel (same data, bit-packed; read back by every mode of this tool)
+            HaploFile::writeBinary(to_binary, genos, genos.idx);
+            if (debug >= 3) printf("Wrote binary panel %s\n", to_binary.c_str());
+            return 0;
+        }
         if (compare) {       // HMC::compare (HMC.cpp:246-257): the first file is the inferred data, the second the target
             if (target.empty()) throw HmcError("Input format " + format + " require 1 filenames! (--compare needs INPUT and TARGET)");
             GenoData tg;
@@ -113,7 +120,8 @@ int main(int argc, char **argv)
             for (size_t i = 0; i < hm.ll_trace.size(); ++i) printf("  iteration %zu: patterns = %d, LL = %f\n", i + 1, hm.npat_trace[i], hm.ll_trace[i]);
             printf("Solving Time = %f (mining %.3f s, device %.3f s, host M-step %.3f s)\n", hm.seconds[0] + hm.seconds[1] + hm.seconds[2], hm.seconds[0], hm.seconds[1], hm.seconds[2]);
         }
-        file.writeGenoData(genos, resolutions, ".reconstructed");
+        if (HaploFile::isBinary(input)) HaploFile::writeBinary(input + ".reconstructed", genos, resolutions);     // output in the input's format
+        else file.writeGenoData(genos, resolutions, ".reconstructed");
         return 0;
     }
     catch (const std::exception &e) {

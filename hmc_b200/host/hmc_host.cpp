@@ -50,6 +50,7 @@ void GenoData::resize(int n, int l)
     position.resize(L);
     for (int i = 0; i < L; ++i) position[i] = i * 1000;     // Constant::average_marker_distance, Constant.cpp:5
     genotype_probability.assign(N, 0.0);
+    packed.clear(); packed_bits = packed_words = 0;
 }
 
 int GenoData::getAlleleIndex(int locus, int value) const
@@ -108,8 +109,130 @@ static bool read_line(FILE *fp, std::string &out)
     return got;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HaploFile: binary panel
+namespace {
+const char HMCB_MAGIC[8] = {'H', 'M', 'C', 'B', '0', '0', '1', '\n'};
+struct HmcbHeader { char magic[8]; int32_t N, L, Amax, bits, words, reserved[3]; };
+
+int bits_for(int Amax) { return Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8); }
+
+void pack_indices(const std::vector<int8_t> &idx, int N, int L, int bits, int words, std::vector<uint32_t> &out)
+{
+    const int per = 32 / (2 * bits);
+    out.assign((size_t) N * words, 0u);
+    for (int i = 0; i < N; ++i) {
+        const int8_t *g0 = &idx[((size_t) i * 2) * L], *g1 = g0 + L;
+        uint32_t *w = &out[(size_t) i * words];
+        for (int l = 0; l < L; ++l) {
+            const uint32_t c = (uint32_t) (g0[l] + 1) | ((uint32_t) (g1[l] + 1) << bits);
+            w[l / per] |= c << ((l % per) * 2 * bits);
+        }
+    }
+}
+
+void unpack_indices(const std::vector<uint32_t> &packed, int N, int L, int bits, int words, std::vector<int8_t> &idx)
+{
+    const int per = 32 / (2 * bits);
+    const uint32_t m = (1u << bits) - 1u;
+    idx.assign((size_t) N * 2 * L, -1);
+    for (int i = 0; i < N; ++i) {
+        const uint32_t *w = &packed[(size_t) i * words];
+        int8_t *g0 = &idx[((size_t) i * 2) * L], *g1 = g0 + L;
+        for (int l = 0; l < L; ++l) {
+            const uint32_t c = w[l / per] >> ((l % per) * 2 * bits);
+            g0[l] = (int8_t) ((int) (c & m) - 1);
+            g1[l] = (int8_t) ((int) ((c >> bits) & m) - 1);
+        }
+    }
+}
+}  // namespace
+
+bool HaploFile::isBinary(const std::string &path)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    char m[8] = {0};
+    const size_t n = fread(m, 1, 8, fp);
+    fclose(fp);
+    return n == 8 && memcmp(m, HMCB_MAGIC, 8) == 0;
+}
+
+void HaploFile::writeBinary(const std::string &path, const GenoData &g, const std::vector<int8_t> &idx)
+{
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) throw HmcError("Can not open file " + path + "!");
+    HmcbHeader h = {};
+    memcpy(h.magic, HMCB_MAGIC, 8);
+    h.N = g.N; h.L = g.L; h.Amax = std::max(g.Amax, 1); h.bits = bits_for(h.Amax);
+    const int per = 32 / (2 * h.bits);
+    h.words = (g.L + per - 1) / per;
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1;
+    ok = ok && fwrite(g.allele_type.data(), 1, g.L, fp) == (size_t) g.L;
+    ok = ok && fwrite(g.position.data(), sizeof(int), g.L, fp) == (size_t) g.L;
+    ok = ok && fwrite(g.n_alleles.data(), sizeof(int32_t), g.L, fp) == (size_t) g.L;
+    std::vector<int32_t> sym((size_t) g.L * h.Amax, -1);
+    for (int l = 0; l < g.L; ++l) for (int j = 0; j < g.n_alleles[l]; ++j) sym[(size_t) l * h.Amax + j] = g.symbols[l][j];
+    ok = ok && fwrite(sym.data(), sizeof(int32_t), sym.size(), fp) == sym.size();
+    ok = ok && fwrite(g.allele_freq.data(), sizeof(double), (size_t) g.L * h.Amax, fp) == (size_t) g.L * h.Amax;
+    for (int i = 0; i < g.N && ok; ++i) {
+        const uint16_t n = (uint16_t) std::min<size_t>(g.ids[i].size(), 65535);
+        ok = fwrite(&n, 2, 1, fp) == 1 && (n == 0 || fwrite(g.ids[i].data(), 1, n, fp) == n);
+    }
+    std::vector<uint32_t> packed;
+    pack_indices(idx, g.N, g.L, h.bits, h.words, packed);
+    ok = ok && fwrite(packed.data(), sizeof(uint32_t), packed.size(), fp) == packed.size();
+    fclose(fp);
+    if (!ok) throw HmcError("Can not write file " + path + "!");
+}
+
+void HaploFile::readBinary(GenoData &g) const
+{
+    FILE *fp = fopen(m_filename.c_str(), "rb");
+    if (!fp) throw HmcError("Can not open file " + m_filename + "!");
+    HmcbHeader h;
+    auto bad = [&](const char *why) { fclose(fp); throw HmcError(std::string("Invalid binary panel (") + why + "): " + m_filename); };
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, HMCB_MAGIC, 8) != 0) bad("header");
+    if (h.N <= 0 || h.L <= 0 || h.Amax < 1 || h.Amax > HMC_MAX_ALLELES || h.bits != bits_for(h.Amax)) bad("dimensions");
+    const int per = 32 / (2 * h.bits);
+    if (h.words != (h.L + per - 1) / per) bad("row length");
+    g.resize(h.N, h.L);
+    g.Amax = h.Amax;
+    if (fread(&g.allele_type[0], 1, h.L, fp) != (size_t) h.L) bad("types");
+    if (fread(g.position.data(), sizeof(int), h.L, fp) != (size_t) h.L) bad("positions");
+    g.n_alleles.assign(h.L, 0);
+    if (fread(g.n_alleles.data(), sizeof(int32_t), h.L, fp) != (size_t) h.L) bad("allele counts");
+    std::vector<int32_t> sym((size_t) h.L * h.Amax);
+    if (fread(sym.data(), sizeof(int32_t), sym.size(), fp) != sym.size()) bad("symbols");
+    g.symbols.assign(h.L, std::vector<int32_t>());
+    for (int l = 0; l < h.L; ++l) {
+        if (g.n_alleles[l] < 0 || g.n_alleles[l] > h.Amax) bad("allele counts");
+        g.symbols[l].assign(sym.begin() + (size_t) l * h.Amax, sym.begin() + (size_t) l * h.Amax + g.n_alleles[l]);
+    }
+    g.allele_freq.assign((size_t) h.L * h.Amax, 0.0);
+    if (fread(g.allele_freq.data(), sizeof(double), g.allele_freq.size(), fp) != g.allele_freq.size()) bad("frequencies");
+    for (int i = 0; i < h.N; ++i) {
+        uint16_t n = 0;
+        if (fread(&n, 2, 1, fp) != 1) bad("ids");
+        g.ids[i].resize(n);
+        if (n && fread(&g.ids[i][0], 1, n, fp) != n) bad("ids");
+    }
+    g.packed_bits = h.bits; g.packed_words = h.words;
+    g.packed.resize((size_t) h.N * h.words);
+    if (fread(g.packed.data(), sizeof(uint32_t), g.packed.size(), fp) != g.packed.size()) bad("genotypes");
+    fclose(fp);
+    unpack_indices(g.packed, h.N, h.L, h.bits, h.words, g.idx);
+    for (int i = 0; i < h.N; ++i) for (int hp = 0; hp < 2; ++hp) for (int l = 0; l < h.L; ++l) {     // raw values as a text reader would have seen them
+        const int k = g.idx[((size_t) i * 2 + hp) * h.L + l];
+        if (k >= g.n_alleles[l]) bad("allele index");
+        g.allele(i, hp, l) = k >= 0 ? g.symbols[l][k] : -1;
+    }
+    g.genotype_probability.assign(h.N, 0.0);
+}
+
 void HaploFile::readGenoData(GenoData &genos) const
 {
+    if (isBinary(m_filename)) { readBinary(genos); return; }
     FILE *fp = fopen(m_filename.c_str(), "r");
     if (!fp) throw HmcError("Can not open file " + m_filename + "!");
     int n = 0, l = 0;
@@ -734,7 +857,11 @@ void HaploBuilder::uploadPanel()
 {
     if (!m_panel_dirty) return;
     const GenoData &genos = *m_genos;
-    ck(ctx(), hmc_set_panel(ctx(), genos.N, genos.L, genos.Amax, genos.idx.data(), genos.n_alleles.data(), genos.allele_freq.data()), "hmc_set_panel");
+    if (!genos.packed.empty())      // read from a binary panel: the rows are already in the device layout
+        ck(ctx(), hmc_set_panel_packed(ctx(), genos.N, genos.L, genos.Amax, genos.packed_bits, genos.packed.data(), genos.n_alleles.data(), genos.allele_freq.data()),
+           "hmc_set_panel_packed");
+    else
+        ck(ctx(), hmc_set_panel(ctx(), genos.N, genos.L, genos.Amax, genos.idx.data(), genos.n_alleles.data(), genos.allele_freq.data()), "hmc_set_panel");
     m_panel_dirty = false;
 }
 

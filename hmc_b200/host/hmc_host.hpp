@@ -34,6 +34,9 @@ public:
     std::vector<double> allele_freq;            // [L][Amax]
     std::vector<int8_t> idx;                    // [N][2][L] allele indices, -1 missing
     std::vector<double> genotype_probability;   // [N], written by resolveAll (HaploModel.cpp:109)
+    // bit-packed indices in the device layout (filled by the binary reader; hmc_set_panel_packed takes them as they are)
+    int packed_bits = 0, packed_words = 0;
+    std::vector<uint32_t> packed;               // [N][packed_words]
 
     void resize(int n, int l);
     int &allele(int i, int h, int l) { return raw[((size_t) i * 2 + h) * L + l]; }
@@ -48,7 +51,13 @@ class HaploFile {
 public:
     explicit HaploFile(const std::string &filename) : m_filename(filename) {}
     const std::string &filename() const { return m_filename; }
-    void readGenoData(GenoData &genos) const;
+    void readGenoData(GenoData &genos) const;   // PHASE text, or the binary panel format below (recognised by its magic)
+    // Binary panel ("HMCB"): header, per-locus symbol tables and frequencies, ids, then the genotypes bit-packed exactly as the
+    // device holds them (2 x bits per locus, code 0 = missing), so ingest is one read + one H2D copy and no text parsing
+    // (PHASE text caps L at ~200 k characters per line, HaploFile.cpp:10, and is tens of GB at C5 scale).
+    static bool isBinary(const std::string &path);
+    void readBinary(GenoData &genos) const;
+    static void writeBinary(const std::string &path, const GenoData &genos, const std::vector<int8_t> &idx);
     // writes allele INDICES `res` ([N][2][L], mapped back through the symbol table) to filename + suffix
     void writeGenoData(const GenoData &genos, const std::vector<int8_t> &res, const char *suffix = "") const;
 };

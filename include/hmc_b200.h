@@ -76,6 +76,15 @@ const char *hmc_version(void);
  * Genotypes are bit-packed on the device (K0). */
 int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, const int32_t *n_alleles, const double *allele_freq);
 
+/* The same for a panel that is already bit-packed in the device layout (binary panel files): per individual
+ * `words` = ceil(L / (32 / (2*bits))) 32-bit words, locus l at bit (l % per) * 2*bits of word l / per, low field = first
+ * allele, each field = allele index + 1 (0 = missing); bits = 2 for Amax <= 3, 4 for Amax <= 15, else 8.  One H2D copy of a
+ * quarter (biallelic) of the unpacked size and no host pass over the genotypes. */
+int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const uint32_t *packed, const int32_t *n_alleles,
+                         const double *allele_freq);
+/* The best resolution of every individual of the last resolve call in the same packed layout: out_packed [count][words]. */
+int hmc_fetch_best_packed(hmc_ctx *ctx, uint32_t *out_packed);
+
 /* The automaton: the HaploPattern fields HaploBuilder reads (HaploPattern.h:19-24,36-37) after
  * PatternManager::initialize (PatternManager.cpp:293-318).  succ: [P][Amax], -1 = NULL successor;
  * alleles: concatenated allele indices, al_off: [P+1]; heads: head_list ids in order

@@ -125,3 +125,58 @@ def test_misuse_is_an_error_code_not_a_crash():
     for i in range(4):
         assert o.individual(2 + i)["pg"] == r["pg"][i]
     dev.close()
+
+
+def test_packed_panel_ingest_and_packed_emission(tmp_path):
+    """A binary (bit-packed) panel goes to the device as it is (hmc_set_panel_packed) and the whole run -- device mining,
+    automaton, resolve -- equals the run from the text panel; `hmc` writes the resolutions of a binary input in binary, and
+    hmc_fetch_best_packed packs the best resolutions on the device exactly like the host packs them."""
+    import ctypes as C
+    import os
+    import subprocess
+    from hmc_b200.build import CLI
+    from hmc_b200.device import lib
+    from hmc_b200.host import HaploModel
+    from hmc_b200.synth import write_phase
+    g = make_panel(70, 90, alleles=5, founders=6, missing=0.04, seed=41)
+    phase, binp = str(tmp_path / "p.phase"), str(tmp_path / "p.hmcb")
+    write_phase(phase, g, kind="M")
+    subprocess.run([CLI, "--to-binary", binp, phase, "-d", "0"], check=True)
+    out = []
+    for path in (phase, binp):
+        hm = HaploModel(max_iteration=3, device_mining=1)
+        hm.load_phase(path)
+        ll, npat = hm.run()
+        out.append((ll, npat, hm.resolutions()))
+        hm.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    # CLI on the binary input: binary output that reads back to the same resolutions as the text run's text output
+    subprocess.run([CLI, phase, "-d", "0", "-i", "3"], check=True)
+    subprocess.run([CLI, binp, "-d", "0", "-i", "3"], check=True)
+    a, b = HaploModel(), HaploModel()
+    a.load_phase(phase + ".reconstructed")
+    b.load_phase(binp + ".reconstructed")
+    with open(binp + ".reconstructed", "rb") as f:
+        assert f.read(4) == b"HMCB"
+    assert np.array_equal(a.panel()[0], b.panel()[0])
+    a.close(); b.close()
+    # device-side packing of the best resolutions
+    o = Oracle(g)
+    o.find_patterns()
+    nall, afreq = o.allele_table()
+    dev = DeviceBuilder()
+    dev.set_panel(g, nall, afreq)
+    dev.set_model(o.export_model())
+    r = dev.resolve_all(K=4)
+    bits = 4
+    per = 32 // (2 * bits)
+    words = (90 + per - 1) // per
+    packed = np.zeros((70, words), np.uint32)
+    rc = lib().hmc_fetch_best_packed(dev._h, packed.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    best = r["haps"][:, 0].astype(np.int64) + 1                    # [N][2][L] codes
+    want = np.zeros((70, words), np.uint64)
+    for l in range(90):
+        want[:, l // per] |= ((best[:, 0, l] | (best[:, 1, l] << bits)).astype(np.uint64)) << np.uint64((l % per) * 2 * bits)
+    assert np.array_equal(packed, want.astype(np.uint32))
+    dev.close()
