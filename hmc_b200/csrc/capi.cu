@@ -855,6 +855,7 @@ int hmc_fetch_patterns(hmc_ctx *ctx, int32_t *start, int32_t *end, double *freq,
     if (!ctx || !start || !end || !freq || !prefix_freq || !tp || !al_off || !alleles) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_fetch_patterns: bad argument") : HMC_ERR_INVALID;
     if (!ctx->mine) return ctx->fail(HMC_ERR_INVALID, "hmc_fetch_patterns before hmc_mine_patterns");
     MinePool &mp = *ctx->mine;
+    if (mp.handed_over) return ctx->fail(HMC_ERR_INVALID, "hmc_fetch_patterns: the list was handed to hmc_build_automaton; fetch before building");
     CK(cudaSetDevice(ctx->device));
     const size_t P = (size_t) mp.P;
     if (P == 0) { al_off[0] = 0; return HMC_OK; }
@@ -885,6 +886,7 @@ int hmc_map_patterns(hmc_ctx *ctx, const hmc_pattern_rec **records, const int8_t
         mp.pin_bytes = cap;
     }
     if (!mp.pin_valid && mp.P > 0) {
+        if (mp.handed_over) return ctx->fail(HMC_ERR_INVALID, "hmc_map_patterns: the list was handed to hmc_build_automaton; map before building");
         CK(cudaMemcpyAsync(mp.pin, mp.o_rec.p, (size_t) mp.P * sizeof(hmc_pattern_rec), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync((char *) mp.pin + rb, mp.o_al.p, (size_t) mp.n_alleles, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

@@ -5,7 +5,9 @@ template <typename T>
 static cudaError_t grow(DevBuf<T> &b, size_t want)
 {
     if (want <= b.n) return cudaSuccess;
-    return b.ensure(std::max<size_t>(want + want / 2, (size_t) 1 << 20));
+    // headroom only while it is cheap: beyond 1 GiB the exact size is taken
+    const size_t bytes = want * sizeof(T);
+    return b.ensure(bytes > ((size_t) 1 << 30) ? want : std::max<size_t>(want + want / 2, (size_t) 1 << 20));
 }
 
 struct MinePool {
@@ -29,6 +31,7 @@ struct MinePool {
     void *pin = nullptr;            // pinned host copy of the records + allele strings (hmc_map_patterns)
     size_t pin_bytes = 0;
     bool pin_valid = false;
+    bool handed_over = false;       // hmc_build_automaton took the list's device arrays for the model (no copy): fetch / map are over
     long long P = 0, n_alleles = 0;
     int panel_serial = -1;          // a0/a1 hold the transposed panel of this hmc_set_panel call
     float ms = 0;
@@ -201,7 +204,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     CK(cudaMemcpyAsync(&P, mp.o_P.p, sizeof P, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    mp.P = P; mp.n_alleles = 0; mp.pin_valid = false;
+    mp.P = P; mp.n_alleles = 0; mp.pin_valid = false; mp.handed_over = false;
     if (P > 0) {
         CK(grow(mp.o_start, P)); CK(grow(mp.o_end, P)); CK(grow(mp.o_node, P)); CK(grow(mp.o_freq, P)); CK(grow(mp.o_prefix, P)); CK(grow(mp.o_tp, P));
         CK(grow(mp.o_len, P)); CK(grow(mp.o_aloff, P + 1));
@@ -225,6 +228,18 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     cudaEventElapsedTime(&mp.ms, ctx->ev[0], ctx->ev[1]);
+    {   // the match lists are scratch: keep them for the next search only while they are small next to the trellis arena
+        size_t bytes = 0;
+        for (int i = 0; i < 2; ++i) bytes += mp.list_id[i].n * sizeof(int) + mp.list_fr[i].n * sizeof(double);
+        if (bytes > ((size_t) 4 << 30)) for (int i = 0; i < 2; ++i) { mp.list_id[i].release(); mp.list_fr[i].release(); }
+        if (mp.node_cap * 43 > ((size_t) 2 << 30)) {     // the trie itself is not needed once the list is emitted
+            cudaFree(mp.nd.parent); cudaFree(mp.nd.start); cudaFree(mp.nd.cnt); cudaFree(mp.nd.cbase); cudaFree(mp.nd.sub); cudaFree(mp.nd.idb);
+            cudaFree(mp.nd.len); cudaFree(mp.nd.flags); cudaFree(mp.nd.al); cudaFree(mp.nd.freq); cudaFree(mp.nd.loff);
+            mp.nd = {}; mp.node_cap = 0;
+            mp.need.release(); mp.need_scan.release(); mp.packed.release(); mp.packed_scan.release(); mp.ext[0].release(); mp.ext[1].release();
+            mp.o_node.release(); mp.o_len.release();
+        }
+    }
     return HMC_OK;
 }
 
@@ -261,13 +276,15 @@ static int run_build_automaton(hmc_ctx *ctx, MinePool &mp, AutPool &ap, int head
     CK(grow(ap.keys, hsize)); CK(grow(ap.vals, hsize)); CK(grow(ap.flags, (size_t) P)); CK(ap.n_sel.ensure(1));
     CK(cudaMemsetAsync(ap.keys.p, 0xFF, hsize * sizeof(u64), st));
     // model arrays of the context
-    CK(grow(ctx->d_succ16, (size_t) P * A)); CK(grow(ctx->d_succ, (size_t) P * A)); CK(grow(ctx->d_start, (size_t) P)); CK(grow(ctx->d_tp, (size_t) P));
-    CK(grow(ctx->d_freq, (size_t) P)); CK(grow(ctx->d_last, (size_t) P)); CK(grow(ctx->d_al_off, (size_t) P + 1)); CK(grow(ctx->d_al, (size_t) mp.n_alleles + 1));
-    CK(cudaMemcpyAsync(ctx->d_start.p, mp.o_start.p, sizeof(int) * P, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_tp.p, mp.o_tp.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_freq.p, mp.o_freq.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_al_off.p, mp.o_aloff.p, sizeof(long long) * (P + 1), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_al.p, mp.o_al.p, (size_t) mp.n_alleles, cudaMemcpyDeviceToDevice, st));
+    if (mp.handed_over) return ctx->fail(HMC_ERR_INVALID, "hmc_build_automaton: this pattern list already became the model");
+    // the list's device arrays BECOME the model's (swap, no copy): start, transition probability, frequency, allele strings
+    mp.o_rec.release();
+    std::swap(ctx->d_start, mp.o_start); std::swap(ctx->d_tp, mp.o_tp); std::swap(ctx->d_freq, mp.o_freq);
+    std::swap(ctx->d_al_off, mp.o_aloff); std::swap(ctx->d_al, mp.o_al);
+    mp.handed_over = true;
+    mp.o_start.release(); mp.o_tp.release(); mp.o_freq.release(); mp.o_aloff.release(); mp.o_al.release();      // the previous model
+    ctx->have_model = false;
+    CK(grow(ctx->d_succ16, (size_t) P * A)); CK(grow(ctx->d_succ, (size_t) P * A)); CK(grow(ctx->d_last, (size_t) P));
     AutParams a = {};
     a.P = P; a.L = L; a.Amax = A; a.start = ctx->d_start.p; a.end = mp.o_end.p; a.al_off = ctx->d_al_off.p; a.al = ctx->d_al.p; a.linfo = ctx->d_linfo.p;
     a.keys = ap.keys.p; a.vals = ap.vals.p; a.hmask = hsize - 1; a.succ = ctx->d_succ.p; a.last = ctx->d_last.p; a.bpow = ap.bpow.p;
