@@ -20,6 +20,8 @@
 #include "compare.cuh"
 #include <cub/cub.cuh>
 #include <climits>
+#include <thread>
+#include <atomic>
 #include "traceback.cuh"
 #include "estep.cuh"
 

@@ -3,27 +3,86 @@
 static int build_trie(hmc_ctx *ctx, EstepTrie &t, int Pc, const int32_t *start, const int64_t *al_off, const int8_t *alleles)
 {
     const int L = ctx->L, A = ctx->Amax;
-    std::vector<int> child((size_t) (L + 1) * A, -1), data(L + 1, -1), root(L + 1);
-    for (int i = 0; i <= L; ++i) root[i] = i;
-    int max_depth = 0;
-    for (int i = 0; i < Pc; ++i) {      // ForwardPatternTree::addPattern, PatternTree.cpp:188-212
-        const int len = (int) (al_off[i + 1] - al_off[i]);
+    // ForwardPatternTree::addPattern (PatternTree.cpp:188-212).  The sub-tries of different start loci share nothing, so they
+    // are built by host threads (candidates bucketed by start, in list order: a later duplicate replaces the earlier one,
+    // Tree.h:87-98) and then laid out one after the other; node i <= L is the root of start locus i.
+    std::vector<int> bucket_off(L + 2, 0);
+    for (int i = 0; i < Pc; ++i) {
+        const long long len = al_off[i + 1] - al_off[i];
         if (start[i] < 0 || len <= 0 || start[i] + len > L) return ctx->fail(HMC_ERR_INVALID, "candidate pattern %d outside the panel", i);
-        int node = root[start[i]];
-        for (int k = 0; k < len; ++k) {
-            const int a = alleles[al_off[i] + k];
-            if (a < 0 || a >= A) return ctx->fail(HMC_ERR_INVALID, "candidate pattern %d holds allele index %d", i, a);
-            int c = child[(size_t) node * A + a];
-            if (c < 0) {
-                c = (int) data.size();
-                data.push_back(-1);
-                child.insert(child.end(), A, -1);
-                child[(size_t) node * A + a] = c;
+        ++bucket_off[start[i] + 1];
+    }
+    for (int l = 0; l <= L; ++l) bucket_off[l + 1] += bucket_off[l];
+    std::vector<int> by_start(Pc), cursor(bucket_off.begin(), bucket_off.end() - 1);
+    for (int i = 0; i < Pc; ++i) by_start[cursor[start[i]]++] = i;
+    struct Sub { std::vector<int> child, data; int max_depth = 0, bad = -1, bad_allele = 0; };
+    std::vector<Sub> subs(L + 1);
+    const int n_threads = (int) std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int st = next.fetch_add(1);
+            if (st > L) break;
+            Sub &sb = subs[st];
+            sb.child.assign(A, -1); sb.data.assign(1, -1);          // local node 0 = the root of this start locus
+            for (int q = bucket_off[st]; q < bucket_off[st + 1]; ++q) {
+                const int i = by_start[q];
+                const int len = (int) (al_off[i + 1] - al_off[i]);
+                int node = 0;
+                for (int k = 0; k < len; ++k) {
+                    const int a = alleles[al_off[i] + k];
+                    if (a < 0 || a >= A) { if (sb.bad < 0) { sb.bad = i; sb.bad_allele = a; } node = -1; break; }
+                    int c = sb.child[(size_t) node * A + a];
+                    if (c < 0) {
+                        c = (int) sb.data.size();
+                        sb.data.push_back(-1);
+                        sb.child.insert(sb.child.end(), A, -1);
+                        sb.child[(size_t) node * A + a] = c;
+                    }
+                    node = c;
+                }
+                if (node >= 0) sb.data[node] = i;
+                sb.max_depth = std::max(sb.max_depth, len);
             }
-            node = c;
         }
-        data[node] = i;     // setChild(i, hp): a later duplicate replaces the earlier one (Tree.h:87-98)
-        max_depth = std::max(max_depth, len);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int q = 1; q < n_threads; ++q) pool.emplace_back(work);
+        work();
+        for (std::thread &th : pool) th.join();
+    }
+    int max_depth = 0;
+    std::vector<long long> base(L + 2, 0);      // global id of local node k > 0 of start st: base[st] + k - 1
+    base[0] = L + 1;
+    for (int st = 0; st <= L; ++st) {
+        if (subs[st].bad >= 0) return ctx->fail(HMC_ERR_INVALID, "candidate pattern %d holds allele index %d", subs[st].bad, subs[st].bad_allele);
+        max_depth = std::max(max_depth, subs[st].max_depth);
+        base[st + 1] = base[st] + (long long) subs[st].data.size() - 1;
+    }
+    if (base[L + 1] > 0x7FFFFFF0ll / std::max(A, 1)) return ctx->fail(HMC_ERR_LIMIT, "candidate trie too large");
+    const size_t n_nodes = (size_t) base[L + 1];
+    std::vector<int> child(n_nodes * A, -1), data(n_nodes, -1), root(L + 1);
+    for (int i = 0; i <= L; ++i) root[i] = i;
+    next = 0;
+    auto place = [&]() {
+        for (;;) {
+            const int st = next.fetch_add(1);
+            if (st > L) break;
+            const Sub &sb = subs[st];
+            const size_t nn = sb.data.size();
+            for (size_t k = 0; k < nn; ++k) {
+                const size_t gid = k == 0 ? (size_t) st : (size_t) (base[st] + (long long) k - 1);
+                data[gid] = sb.data[k];
+                for (int a = 0; a < A; ++a) { const int c = sb.child[k * A + a]; child[gid * A + a] = c < 0 ? -1 : (int) (base[st] + c - 1); }
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int q = 1; q < n_threads; ++q) pool.emplace_back(place);
+        place();
+        for (std::thread &th : pool) th.join();
     }
     if (max_depth > ESTEP_MAX_DEPTH) return ctx->fail(HMC_ERR_LIMIT, "pattern length %d exceeds %d", max_depth, ESTEP_MAX_DEPTH);
     CK(t.d_root.ensure(root.size())); CK(t.d_child.ensure(child.size())); CK(t.d_data.ensure(data.size()));
