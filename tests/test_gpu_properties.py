@@ -84,3 +84,30 @@ def test_forward_backward_identity_and_estep_mass(c2):
     assert np.allclose(mass, n, rtol=1e-9)
     # a pattern can never be more frequent than its prefix
     assert (f <= pf * (1 + 1e-9) + 1e-12).all()
+
+
+def test_device_mined_model_equals_host_mined_model_at_full_size(c2):
+    """K5 + K6 at C2's full size (4.7 M patterns, 9.4 M trie nodes): the model the fixture built on the device must be the one
+    the threaded host miner + host automaton build produce, bit for bit (ids, strings, frequencies, successors, heads)."""
+    assert c2["hm"].mined_on_device()
+    hm0 = HaploModel(device_mining=0)
+    hm0.set_panel(c2["g"], "S")
+    hm0.build()
+    assert not hm0.mined_on_device()
+    a, b = c2["m"], hm0.export_model()
+    hm0.close()
+    assert a["P"] == b["P"] and a["head_len"] == b["head_len"]
+    for k in ("start", "end", "freq", "prefix", "tp", "succ", "heads", "al", "al_off"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_switch_error_of_the_c2_run_is_small_and_symmetric(c2):
+    """K7 at full size: the panel holds the true phase, so HaploComp of the best resolutions against it is the phasing error of
+    the run; comparing where the resolutions lie on the device equals comparing a host copy, and swapping the two haplotype
+    rows of every inferred individual changes nothing (switch distance and genotype difference are orientation-free)."""
+    g, dev, r = c2["g"], c2["dev"], c2["r10"]
+    best = np.ascontiguousarray(r["haps"][:, 0])
+    a = dev.compare(g, best)
+    b = dev.compare(g, np.ascontiguousarray(best[:, ::-1]))
+    assert np.array_equal(a["counts"], b["counts"])
+    assert 0.0 <= a["switch_error"] < 0.2 and a["counts"][1] > 0
