@@ -295,7 +295,7 @@ def run_ours(args):
         "exact_epass": epass,
         "mstep": mstep,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -335,7 +335,7 @@ def run_reference(args):
     g, kind, n_ind, n_loci = make_workload(0)
     ref = os.path.join(ROOT, "oracle", "_ref", "hmc_ref")
     if not os.path.exists(ref):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/hmc_ref was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/hmc_ref was not built (needs /root/reference at build time)"})
         return
     tmp = os.environ.get("TMPDIR", "/tmp")
     phase = os.path.join(tmp, f"hmc_bench_{WORKLOAD}_{n_ind}x{n_loci}.phase")
@@ -361,7 +361,7 @@ def run_reference(args):
         worst = max(worst, float(np.mean(j["resolve_s"])))
         build_s = max(build_s, j["build_s"])
     if steps_total == 0 or worst <= 0:
-        print(json.dumps({"impl": "reference", "unavailable": "hmc_ref produced no timing"}))
+        emit({"impl": "reference", "unavailable": "hmc_ref produced no timing"})
         return
     value = steps_total / worst
     sample = (f"{procs_n} processes x first-come slices of {per} individuals x {n_loci} loci of the C2 panel, full-panel model mined by each process "
@@ -374,10 +374,28 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": procs_n, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # Native libraries write to file descriptor 1 on their own (NCCL prints its version banner there when the first communicator is
+    # created): keep the real stdout for the JSON line and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
