@@ -19,6 +19,7 @@
 #include "automaton.cuh"
 #include "compare.cuh"
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <climits>
 #include <thread>
 #include <atomic>

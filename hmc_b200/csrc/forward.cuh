@@ -363,9 +363,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
                 // ---- pass B+C: creators in ordinal order -> new state indices and arrival-segment offsets ----
                 // each lane owns UB consecutive ordinals, so the loads of a lane are independent and one block scan serves UB*NT slots
-                int n_arr = 0, n_heavy = 0;
-                constexpr int UB = 4, HEAVY_N = 3;
-                const int ocap = FAST ? CC : sc.scap;
+                int n_arr = 0;
+                constexpr int UB = 4;
                 for (int base = 0; base < C; base += NT * UB) {
                     const int c0 = base + tid * UB;
                     int enc[UB], nn[UB];
@@ -378,21 +377,19 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & 0x3FFFFFFF] : 0xFFFFFFFFu;
-                    int ncr = 0, nar = 0, nhv = 0;
+                    int ncr = 0, nar = 0;
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
                         nn[u] = cr[u] ? (int) cnt[enc[u] & 0x3FFFFFFF] : 0;
                         ncr += cr[u] ? 1 : 0;
-                        nhv += nn[u] >= HEAVY_N ? 1 : 0;
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) nar += nn[u];
-                    // one scan for all three: heavy creators | creators | arrivals
+                    // one scan for both: creators | arrivals
                     long long tot;
-                    const long long ex = BlockScan<NT>::run(((long long) nhv << 52) | ((long long) ncr << 40) | (long long) nar, tot, sm.tmp);
+                    const long long ex = BlockScan<NT>::run(((long long) ncr << 40) | (long long) nar, tot, sm.tmp);
                     int idx = S_out + (int) ((ex >> 40) & 0xFFF), off = n_arr + (int) (ex & 0xFFFFFFFFFFll);
-                    int hv = n_heavy + (int) (ex >> 52);
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         if (cr[u]) {
@@ -408,7 +405,6 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     }
                     S_out += (int) ((tot >> 40) & 0xFFF);
                     n_arr += (int) (tot & 0xFFFFFFFFFFll);
-                    n_heavy += (int) (tot >> 52);
                 }
                 if (S_out == 0) return 1;       // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82
                 if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; return 2; }

@@ -67,9 +67,11 @@ __global__ void mine_roots_kernel(MineParams m, long long *need, long long *pack
 template <bool SAMPLES, bool FILL>
 __global__ void __launch_bounds__(256) mine_sweep_kernel(MineParams m, int n_ext, int par)
 {
+    __shared__ double s_val[SAMPLES && !FILL ? 8 : 1][32];     // sampling COUNT: the weights of the current 32 entries, per warp
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const u32 lt = (1u << lane) - 1u;
+    double *const sv = s_val[SAMPLES && !FILL ? (threadIdx.x >> 5) : 0];
     for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_ext; k += warps) {
         const int p = m.ext[k];
         const int start = m.nd.start[p], plen = m.nd.len[p], e = start + plen;
@@ -102,6 +104,22 @@ __global__ void __launch_bounds__(256) mine_sweep_kernel(MineParams m, int n_ext
                 if (SAMPLES) { if (!FILL) wv = m.w[i]; }
                 else { y = a1[i]; if (!full) pf = frs[q]; }
             }
+            if constexpr (SAMPLES && !FILL) {
+                // a sample's weight does not depend on the child: park the 32 weights in shared memory, collect child j's members
+                // as a ballot mask in lane j, and let every child lane add its own terms in list order -- the chains of the
+                // children run side by side instead of one shuffle + predicated add per term for the whole warp
+                sv[lane] = wv;
+                u32 mine = 0u;
+                for (int j = 0; j < A; ++j) {
+                    if (!((am >> j) & 1u)) continue;
+                    const u32 mask = __ballot_sync(0xffffffffu, valid && (x < 0 || x == j));
+                    if (lane == j) { mine = mask; cnt += __popc(mask); }
+                }
+                __syncwarp();
+                while (mine) { const int b = __ffs(mine) - 1; mine &= mine - 1; total += sv[b]; }
+                __syncwarp();
+            }
+            else
             for (int j = 0; j < A; ++j) {
                 if (!((am >> j) & 1u)) continue;
                 bool emit;

@@ -277,13 +277,25 @@ static int run_build_automaton(hmc_ctx *ctx, MinePool &mp, AutPool &ap, int head
     CK(cudaMemsetAsync(ap.keys.p, 0xFF, hsize * sizeof(u64), st));
     // model arrays of the context
     if (mp.handed_over) return ctx->fail(HMC_ERR_INVALID, "hmc_build_automaton: this pattern list already became the model");
-    // the list's device arrays BECOME the model's (swap, no copy): start, transition probability, frequency, allele strings
-    mp.o_rec.release();
-    std::swap(ctx->d_start, mp.o_start); std::swap(ctx->d_tp, mp.o_tp); std::swap(ctx->d_freq, mp.o_freq);
-    std::swap(ctx->d_al_off, mp.o_aloff); std::swap(ctx->d_al, mp.o_al);
-    mp.handed_over = true;
-    mp.o_start.release(); mp.o_tp.release(); mp.o_freq.release(); mp.o_aloff.release(); mp.o_al.release();      // the previous model
     ctx->have_model = false;
+    if ((size_t) P * 28 + (size_t) mp.n_alleles > ((size_t) 2 << 30)) {
+        // large lists: their device arrays BECOME the model's (swap, no copy, nothing held twice): start, transition probability,
+        // frequency, allele strings; fetch / map are over for this list
+        mp.o_rec.release();
+        std::swap(ctx->d_start, mp.o_start); std::swap(ctx->d_tp, mp.o_tp); std::swap(ctx->d_freq, mp.o_freq);
+        std::swap(ctx->d_al_off, mp.o_aloff); std::swap(ctx->d_al, mp.o_al);
+        mp.handed_over = true;
+        mp.o_start.release(); mp.o_tp.release(); mp.o_freq.release(); mp.o_aloff.release(); mp.o_al.release();      // the previous model
+    }
+    else {      // small lists: copy, so that neither side reallocates from one EM iteration to the next
+        CK(grow(ctx->d_start, (size_t) P)); CK(grow(ctx->d_tp, (size_t) P)); CK(grow(ctx->d_freq, (size_t) P));
+        CK(grow(ctx->d_al_off, (size_t) P + 1)); CK(grow(ctx->d_al, (size_t) mp.n_alleles + 1));
+        CK(cudaMemcpyAsync(ctx->d_start.p, mp.o_start.p, sizeof(int) * P, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_tp.p, mp.o_tp.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_freq.p, mp.o_freq.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_al_off.p, mp.o_aloff.p, sizeof(long long) * (P + 1), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_al.p, mp.o_al.p, (size_t) mp.n_alleles, cudaMemcpyDeviceToDevice, st));
+    }
     CK(grow(ctx->d_succ16, (size_t) P * A)); CK(grow(ctx->d_succ, (size_t) P * A)); CK(grow(ctx->d_last, (size_t) P));
     AutParams a = {};
     a.P = P; a.L = L; a.Amax = A; a.start = ctx->d_start.p; a.end = mp.o_end.p; a.al_off = ctx->d_al_off.p; a.al = ctx->d_al.p; a.linfo = ctx->d_linfo.p;
@@ -300,7 +312,7 @@ static int run_build_automaton(hmc_ctx *ctx, MinePool &mp, AutPool &ap, int head
     CK(grow(ctx->d_head_lut, (size_t) size));
     {
         size_t bytes = 0;
-        cub::CountingInputIterator<int> ids(0);
+        thrust::counting_iterator<int> ids(0);
         CK(cub::DeviceSelect::Flagged(nullptr, bytes, ids, ap.flags.p, ctx->d_heads.p, ap.n_sel.p, (int) P, st));
         CK(grow(ap.cub_tmp, bytes + 16));
         CK(cub::DeviceSelect::Flagged(ap.cub_tmp.p, bytes, ids, ap.flags.p, ctx->d_heads.p, ap.n_sel.p, (int) P, st));

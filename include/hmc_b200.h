@@ -161,8 +161,8 @@ int hmc_map_patterns(hmc_ctx *ctx, const hmc_pattern_rec **records, const int8_t
 /* K6: PatternManager::initialize (PatternManager.cpp:293-318) over the list of the last hmc_mine_patterns call, on the
  * device: successor table by longest trailing match with start >= the pattern's start (PatternTree.cpp:98-134), head
  * list (:303-306); the result is installed as the context's model exactly as hmc_set_model would (no host round trip).
- * The list's device arrays become the model's (no copy): hmc_fetch_patterns / hmc_map_patterns must come BEFORE this call
- * (a view already mapped stays valid).
+ * Large lists (> 2 GB) are not copied: their device arrays become the model's, so hmc_fetch_patterns / hmc_map_patterns must
+ * come BEFORE this call (a view already mapped stays valid).
  * hmc_fetch_automaton copies succ [P][Amax] and heads [n_heads] out for parity checks / export; either may be NULL. */
 int hmc_build_automaton(hmc_ctx *ctx, int head_len, int32_t *out_n_heads);
 int hmc_fetch_automaton(hmc_ctx *ctx, int32_t *succ, int32_t *heads);
