@@ -180,3 +180,22 @@ def test_packed_panel_ingest_and_packed_emission(tmp_path):
         want[:, l // per] |= ((best[:, 0, l] | (best[:, 1, l] << bits)).astype(np.uint64)) << np.uint64((l % per) * 2 * bits)
     assert np.array_equal(packed, want.astype(np.uint32))
     dev.close()
+
+
+@pytest.mark.parametrize("threads", [1, 32, 64, 128])
+@pytest.mark.parametrize("K", [12, 16, 25, 32])
+def test_sample_sizes_above_ten(K, threads):
+    """--sample-size up to the documented limit of 32 runs the KMAX = 16 / 32 instantiations of every forward variant."""
+    from test_gpu_forward import klist_equiv
+    g = make_panel(24, 40, founders=6, missing=0.05, seed=50 + K)
+    o, ll, dev, r = both(g, K=K, threads=threads)
+    assert ll == r["ll"]
+    most = 0
+    for i in range(24):
+        a = o.individual(i)
+        assert a["pg"] == r["pg"][i] and a["n"] == r["nres"][i]
+        klist_equiv(r["prior"][i, :a["n"]], r["haps"][i, :a["n"]], a["prior"], a["haps"])
+        assert np.all(np.diff(r["prior"][i, :a["n"]]) <= 0)
+        most = max(most, a["n"])
+    assert most > 10                                        # the long lists are really exercised
+    dev.close()
