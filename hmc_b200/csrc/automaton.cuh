@@ -33,7 +33,8 @@ struct AutParams {
 
 __device__ __forceinline__ u64 aut_key(u64 hstr, int start, int end)
 {
-    u64 k = mix64(hstr ^ ((u64) (u32) start << 32) ^ (u64) (u32) end * 0xD6E8FEB86659FD93ull);
+    u64 k = hstr ^ ((u64) (u32) start << 32) ^ (u64) (u32) end * 0xD6E8FEB86659FD93ull;
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;     // full 64-bit finaliser
     return k == AUT_EMPTY ? 0 : k;
 }
 
