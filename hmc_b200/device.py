@@ -122,13 +122,21 @@ class DeviceBuilder:
         r["haps"] = np.zeros((count, K, 2, self.L), np.int8) if haps else None
         return r
 
-    def resolve_all(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0, haps: bool = True) -> dict:
+    def resolve_all(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0, haps: bool = True, out: dict | None = None) -> dict:
+        """`out`: caller-owned result arrays as returned by `alloc_results` (e.g. page-locked), filled in place -- the C-ABI writes
+        into caller buffers; without it fresh arrays are allocated per call."""
         count = self.N - first if count is None else count
-        r = self._alloc(count, K, haps)
+        r = dict(out) if out is not None else self._alloc(count, K, haps)
+        if out is not None:
+            assert r["prior"].shape == (count, K) and r["pg"].shape == (count,) and (r["haps"] is None or r["haps"].shape == (count, K, 2, self.L))
+            r["ll"] = np.zeros(1)
         self._ck(lib().hmc_resolve_all(self._h, first, count, K, flags, _p(r["pg"]), _p(r["exp"]), _p(r["coverage"]), _p(r["nres"]),
                                        _p(r["prior"]), _p(r["posterior"]), _p(r["haps"]), _p(r["ll"])))
         r["ll"] = float(r["ll"][0])
         return r
+
+    def alloc_results(self, count: int, K: int, haps: bool = True) -> dict:
+        return self._alloc(count, K, haps)
 
     def resolve_all_device(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0):
         count = self.N - first if count is None else count
