@@ -756,29 +756,33 @@ void PatternManager::extendPatterns(PatternSet &patterns, std::vector<int> &seed
 {
     const GenoData &g = *m_builder.genos();
     const int L = g.L;
-    struct S { int start; std::vector<int8_t> al; double freq; };
-    std::vector<S> cur, nxt;
-    for (int sidx : last_seeds) { const Pattern &p = last.pats[sidx]; cur.push_back(S{p.start, std::vector<int8_t>(last.al(p), last.al(p) + p.length()), p.frequency}); }
-    std::vector<int> cur_idx;
+    // level 0 walks the seeds of the last round (in `last`), the later levels the patterns this call has just added (in
+    // `patterns`); a candidate is (set, index): its string is read where it lies and copied once into the child
+    std::vector<int> cur(last_seeds), nxt;
+    const PatternSet *from = &last;
+    std::vector<int8_t> buf;
+    size_t room = 0;
+    for (int sidx : last_seeds) room += (size_t) last.pats[sidx].length() + 1;
+    patterns.alleles.reserve(patterns.alleles.size() + room * 4);
     int level = 4;
     while (level-- > 0) {
-        nxt.clear(); cur_idx.clear();
-        for (const S &hp : cur) {
-            const int end = hp.start + (int) hp.al.size();
-            if (end < L && (int) hp.al.size() < m_max_len[hp.start]) {
-                if (hp.freq >= m_min_freq) {
-                    for (int j = 0; j < g.n_alleles[end]; ++j) {
-                        S n{hp.start, hp.al, hp.freq};
-                        n.al.push_back((int8_t) j);
-                        cur_idx.push_back(patterns.add(n.start, n.al.data(), (int) n.al.size(), n.freq, 1.0, 1.0));
-                        nxt.push_back(std::move(n));
-                    }
+        nxt.clear();
+        for (int idx : cur) {
+            const Pattern hp = from->pats[idx];         // by value: `patterns` grows below
+            const int len = hp.length(), end = hp.end;
+            if (end < L && len < m_max_len[hp.start] && hp.frequency >= m_min_freq) {
+                buf.assign(from->al(hp), from->al(hp) + len);
+                buf.push_back(0);
+                for (int j = 0; j < g.n_alleles[end]; ++j) {
+                    buf[len] = (int8_t) j;
+                    nxt.push_back(patterns.add(hp.start, buf.data(), len + 1, hp.frequency, 1.0, 1.0));
                 }
             }
         }
         cur.swap(nxt);
+        from = &patterns;
     }
-    seeds = cur_idx;        // the last level's new patterns are the next round's seeds
+    seeds = cur;            // the last level's new patterns are the next round's seeds
 }
 
 void PatternManager::estimatePatterns()
@@ -789,11 +793,14 @@ void PatternManager::estimatePatterns()
     PatternSet patterns, candidates;
     std::vector<int> seeds;
     const std::vector<int32_t> &succ = successors();
+    const double t_begin = now_s();
+    std::vector<int8_t> al;
+    patterns.pats.reserve((size_t) size() * 2); patterns.alleles.reserve(m_patterns.alleles.size() * 2 + (size_t) size());
     for (int i = 0; i < size(); ++i) {
         const Pattern &hp = m_patterns.pats[i];
         patterns.add(hp.start, m_patterns.al(hp), hp.length(), hp.frequency, hp.prefix_freq, hp.transition_prob);
         if (hp.end < L && hp.length() < m_max_len[hp.start]) {
-            std::vector<int8_t> al(m_patterns.al(hp), m_patterns.al(hp) + hp.length());
+            al.assign(m_patterns.al(hp), m_patterns.al(hp) + hp.length());
             al.push_back(0);
             for (int j = 0; j < g.n_alleles[hp.end]; ++j) {
                 const int s = succ[(size_t) i * A + j];
@@ -804,12 +811,25 @@ void PatternManager::estimatePatterns()
             }
         }
     }
+    const bool timing = getenv("HMC_B200_HOST_TIMING") != nullptr;
+    double t_mark = now_s();
+    if (timing) fprintf(stderr, "[host] estimatePatterns: %d patterns + %zu unseen extensions prepared in %.3f s\n", size(), seeds.size(), t_mark - t_begin);
     while (!patterns.pats.empty()) {
         m_builder.estimateFrequency(patterns);
-        for (const Pattern &p : patterns.pats) candidates.add(p.start, patterns.al(p), p.length(), p.frequency, p.prefix_freq, p.transition_prob);
+        const double t_e = now_s();
+        {   // candidates += patterns (same order), strings appended in one piece
+            const int64_t shift = (int64_t) candidates.alleles.size();
+            candidates.alleles.insert(candidates.alleles.end(), patterns.alleles.begin(), patterns.alleles.end());
+            const size_t n0 = candidates.pats.size();
+            candidates.pats.insert(candidates.pats.end(), patterns.pats.begin(), patterns.pats.end());
+            for (size_t q = n0; q < candidates.pats.size(); ++q) candidates.pats[q].al += shift;
+        }
         PatternSet next;
         std::vector<int> next_seeds;
         extendPatterns(next, next_seeds, patterns, seeds);
+        if (timing) fprintf(stderr, "[host]   E-pass over %zu candidates %.3f s, collect + extend %.3f s -> %zu new candidates\n", patterns.size(), t_e - t_mark,
+                            now_s() - t_e, next.size());
+        t_mark = now_s();
         patterns = std::move(next);
         seeds = std::move(next_seeds);
     }
@@ -817,7 +837,9 @@ void PatternManager::estimatePatterns()
     for (const Pattern &hp : candidates.pats)
         if (hp.frequency >= m_min_freq || hp.length() <= m_min_len[hp.start])
             m_patterns.add(hp.start, candidates.al(hp), hp.length(), hp.frequency, hp.prefix_freq, hp.transition_prob);
+    const double t_i = now_s();
     initialize();
+    if (timing) fprintf(stderr, "[host]   selection %.3f s, initialize %.3f s, %d patterns kept\n", t_i - t_mark, now_s() - t_i, size());
 }
 
 // ---------------------------------------------------------------------------------------------
