@@ -169,12 +169,15 @@ struct EstepParams {
 
 constexpr int ESTEP_MAX_DEPTH = 160;
 constexpr int ESTEP_WARPS = 4;
+#ifndef ESTEP_MINB
+#define ESTEP_MINB 8
+#endif
 
 // K4: one warp per (individual, start) task: depth-first walk of the candidate trie below root(start) with the three
 // sparse weight vectors of HaploBuilder.cpp:334-450 ([0] both haplotypes match so far, [1] only the a-role one,
 // [2] only the b-role one) kept as an entry stack; a node's entries are produced from its parent's by a scatter into
 // dense accumulators plus a first-touch list.  Subtrees below a node with no entry are skipped: they only ever add 0.
-__global__ void __launch_bounds__(ESTEP_WARPS * 32) estep_kernel(EstepParams p)
+__global__ void __launch_bounds__(ESTEP_WARPS * 32, ESTEP_MINB) estep_kernel(EstepParams p)
 {
     __shared__ int s_node[ESTEP_WARPS][ESTEP_MAX_DEPTH], s_iter[ESTEP_WARPS][ESTEP_MAX_DEPTH];
     __shared__ int s_off[ESTEP_WARPS][ESTEP_MAX_DEPTH + 1];
