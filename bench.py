@@ -217,8 +217,14 @@ def run_ours(args):
         if world > 1:
             t = torch.tensor([ep_elapsed], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ep_elapsed = float(t.item())
             s2 = torch.tensor([ep_steps], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(s2); ep_steps = float(s2.item())
+        entries = int(dev.counters()["estep_entries"])
+        k4_bytes = 32.0 * entries + 16.0 * int(model["P"])          # re-read of the matched states per visited node + the count vector
+        peak_k4, _ = peaks()
         epass = {"value": ep_steps / ep_elapsed, "unit": "steps/s", "seconds": ep_elapsed, "candidates": int(model["P"]),
                  "kernel_ms": {"forward": kms["forward"], "backward": kms["backward"], "estep": kms["estep"]},
+                 "roofline": {"bound": "hbm", "kernel": "estep (K4), this rank", "entries": entries, "algorithmic_bytes_per_launch": k4_bytes,
+                              "achieved": k4_bytes / (kms["estep"] * 1e-3) / 1e9, "peak": peak_k4, "unit": "GB/s",
+                              "frac": k4_bytes / (kms["estep"] * 1e-3) / 1e9 / peak_k4},
                  "exchange": "all-reduce(sum) of 2*P fp64 raw counts" if world > 1 else "none (1 GPU)",
                  "note": "one pass, includes the host-side trie flattening and the H2D of the candidate list"}
 

@@ -95,6 +95,7 @@ struct hmc_ctx {
     DevBuf<double> d_tp, d_freq;
     DevBuf<unsigned char> d_last;
     DevBuf<int> d_end_tmp, d_model_err, d_miss;
+    DevBuf<double> d_counts_snap;
     DevBuf<long long> d_al_off;
     DevBuf<signed char> d_al;
 
@@ -502,7 +503,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             fprintf(stderr, "%s pass Mcycles: [0] %lld  [1] %lld  [2] %lld  [3] %lld  [4] %lld  [5] %lld  [7] %lld | [6] %lld\n", b == 8 ? "fast " : "spill",
                     hc[b] >> 20, hc[b + 1] >> 20, hc[b + 2] >> 20, hc[b + 3] >> 20, hc[b + 4] >> 20, hc[b + 5] >> 20, hc[b + 7] >> 20, hc[b + 6]);
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
-    ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5];
+    ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
     ctx->last_K = K; ctx->last_estep = estep;
     return HMC_OK;
@@ -541,7 +542,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
-    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release(); ctx->d_miss.release();
+    ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release(); ctx->d_miss.release(); ctx->d_counts_snap.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
     ctx->d_wave.release(); ctx->d_status.release(); ctx->d_final_exp.release(); ctx->d_locus_exp.release();
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();

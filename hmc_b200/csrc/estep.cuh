@@ -165,6 +165,7 @@ struct EstepParams {
     int Pc;
     int *queue;
     int *error;             // set when an entry stack overflowed
+    unsigned long long *work;   // parent entries read by the walk (HMC_CNT_ESTEP_ENTRIES)
 };
 
 constexpr int ESTEP_MAX_DEPTH = 160;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32, ESTEP_MINB) estep_kernel(Est
     int *node_st = s_node[wi], *iter_st = s_iter[wi], *off_st = s_off[wi];
     double *freq_st = s_freq[wi];
     const long long n_tasks = (long long) p.n_wave * L;
+    unsigned long long work = 0;
 
     for (;;) {
         long long task = 0;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32, ESTEP_MINB) estep_kernel(Est
             const int locus = start + depth;            // the locus this child's allele j sits at
             const int e0 = off_st[depth], e1 = off_st[depth + 1];
             const int out0 = e1;
+            work += (unsigned long long) (e1 - e0);
             int n_out = 0;
             double fsum = 0.0;
             int corr = 0;
@@ -346,6 +349,7 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32, ESTEP_MINB) estep_kernel(Est
         }
         __syncwarp();
     }
+    if (lane == 0 && work) atomicAdd(p.work, work);
 }
 
 }  // namespace hmc

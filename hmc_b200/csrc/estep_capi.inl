@@ -128,7 +128,7 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         ++launches;
         // K4: scratch sized from the largest live-state set of this wave
-        long long hc[4];
+        long long hc[8];
         CK(cudaMemcpyAsync(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         const int smax = (int) std::max<long long>(hc[2], 1);
@@ -164,9 +164,9 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
             ep.status = ctx->d_status.p; ep.aexp = scaled ? ctx->d_locus_exp.p : nullptr; ep.bexp = scaled ? d_bexp.p : nullptr; ep.final_exp = ctx->d_final_exp.p;
             ep.pg = ctx->d_pgin.p; ep.pg_exp = pg_exp ? ctx->d_pgexp.p : nullptr; ep.first = first; ep.n_wave = n_wave; ep.scratch = d_edesc.p;
             ep.counts = ctx->d_counts.p; ep.Pc = Pc; ep.queue = d_eflags.p; ep.error = d_eflags.p + 2;
+            ep.work = (unsigned long long *) (ctx->d_counters.p + 7);
             // the counts of a failed attempt must not be kept: snapshot and restore
-            DevBuf<double> snap;
-            if (attempt == 0) { /* first attempt accumulates straight into d_counts; a retry needs the pre-wave values */ }
+            DevBuf<double> &snap = ctx->d_counts_snap;
             CK(snap.ensure((size_t) 2 * Pc));
             CK(cudaMemcpyAsync(snap.p, ctx->d_counts.p, sizeof(double) * 2 * Pc, cudaMemcpyDeviceToDevice, ctx->stream));
             CK(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -180,11 +180,11 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); if (attempt == 0) ctx->kernel_ms[2] += ms;
             cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->kernel_ms[3] += ms;
-            if (eflags[2] == 0) { snap.release(); return HMC_OK; }
-            if (eflags[2] == 2) { snap.release(); return ctx->fail(HMC_ERR_LIMIT, "candidate trie deeper than %d", ESTEP_MAX_DEPTH); }
+            if (eflags[2] == 0) return HMC_OK;
+            if (eflags[2] == 2) return ctx->fail(HMC_ERR_LIMIT, "candidate trie deeper than %d", ESTEP_MAX_DEPTH);
             CK(cudaMemcpyAsync(ctx->d_counts.p, snap.p, sizeof(double) * 2 * Pc, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_counters.p + 7, &hc[7], sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));     // entry counter of the failed attempt
             CK(cudaStreamSynchronize(ctx->stream));
-            snap.release();
             ecap *= 4;
         }
         return ctx->fail(HMC_ERR_LIMIT, "E-step entry stack overflow");

@@ -16,7 +16,7 @@ _LIB = None
 
 FLAG_SCALED = 1
 FLAG_KEEP_TRELLIS = 2
-CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps", "launches", "_")
+CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps", "launches", "estep_entries")
 
 EXPORTS = [
     "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",

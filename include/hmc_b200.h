@@ -61,6 +61,7 @@ typedef enum hmc_status {
 #define HMC_CNT_WAVES       4       /* arena waves used by the last call */
 #define HMC_CNT_SPILL_STEPS 5       /* steps that left the shared-memory fast path */
 #define HMC_CNT_LAUNCHES    6       /* kernels launched by the last call */
+#define HMC_CNT_ESTEP_ENTRIES 7     /* E-step: (node, matched state, class) entries read by the trie walk (K4 traffic model) */
 #define HMC_CNT_N           8
 
 /* Create a context on CUDA device `device`.  arena_bytes = 0 picks ~60% of free device memory for
