@@ -5,7 +5,12 @@ import numpy as np
 from hmc_b200 import HaploModel, DeviceBuilder
 from hmc_b200.synth import make_config
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-g, kind = make_config(cfg)
+if cfg == "custom":     # custom N L alleles founders missing
+    from hmc_b200.synth import make_panel
+    n_, l_, a_, f_, m_ = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), float(sys.argv[6])
+    g, kind = make_panel(n_, l_, alleles=a_, founders=f_, missing=m_, seed=4), ("M" if a_ > 2 else "S")
+else:
+    g, kind = make_config(cfg)
 hm = HaploModel(device_mining=0); hm.set_panel(g, kind)
 t = time.time(); hm.build(); print(f"host threads: mining + automaton {time.time() - t:.3f} s", flush=True)
 idx, na, af = hm.panel()
