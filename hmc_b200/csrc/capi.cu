@@ -96,6 +96,9 @@ struct hmc_ctx {
     DevBuf<unsigned char> d_last;
     DevBuf<int> d_end_tmp, d_model_err, d_miss;
     DevBuf<double> d_counts_snap;
+    // E-step trellis of the last single-wave hmc_estimate_counts call (alpha, beta, forward links stay in the arena): the E-passes of one
+    // M-step differ only in their candidate list, so K1 + K3 run once and the later passes go straight to K4
+    struct EstepCache { bool valid = false; int first = 0, count = 0, n_wave = 0; unsigned flags = 0; FwdParams fp; int64_t counters[HMC_CNT_N]; } ecache;
     DevBuf<long long> d_al_off;
     DevBuf<signed char> d_al;
 
@@ -396,6 +399,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     CK(ctx->d_cursor.ensure(1));
     CK(ctx->d_flags.ensure(2));
     CK(ctx->d_counters.ensure(24));
+    ctx->ecache.valid = false;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 24 * sizeof(long long), ctx->stream));
     memset(ctx->counters, 0, sizeof ctx->counters);
     memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
@@ -506,6 +510,11 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
     ctx->last_K = K; ctx->last_estep = estep;
+    if (estep && waves == 1) {
+        ctx->ecache.first = first; ctx->ecache.count = count; ctx->ecache.flags = flags; ctx->ecache.fp = fp; ctx->ecache.n_wave = fp.n_wave;
+        memcpy(ctx->ecache.counters, ctx->counters, sizeof ctx->counters);
+        ctx->ecache.valid = true;
+    }
     return HMC_OK;
 }
 
@@ -565,6 +574,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     if (!ctx || N <= 0 || L <= 0 || !geno || !n_alleles || !allele_freq) return ctx ? ctx->fail(HMC_ERR_INVALID, "hmc_set_panel: bad argument") : HMC_ERR_INVALID;
     if (Amax < 1 || Amax > HMC_MAX_ALLELES) return ctx->fail(HMC_ERR_LIMIT, "Amax %d outside [1,%d]", Amax, HMC_MAX_ALLELES);
     CK(cudaSetDevice(ctx->device));
+    ctx->ecache.valid = false;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax;
     ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
     const int per = 32 / (2 * ctx->bits);
@@ -616,6 +626,7 @@ int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const u
     if (Amax < 1 || Amax > HMC_MAX_ALLELES) return ctx->fail(HMC_ERR_LIMIT, "Amax %d outside [1,%d]", Amax, HMC_MAX_ALLELES);
     if (bits != (Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8))) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel_packed: %d bits per allele do not match Amax %d", bits, Amax);
     CK(cudaSetDevice(ctx->device));
+    ctx->ecache.valid = false;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
     const int per = 32 / (2 * bits);
     ctx->words = (L + per - 1) / per;
@@ -661,6 +672,7 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
     if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_model before hmc_set_panel");
     if (head_len < 1 || head_len > 8 || head_len > ctx->L) return ctx->fail(HMC_ERR_LIMIT, "head length %d outside [1,8]", head_len);
     CK(cudaSetDevice(ctx->device));
+    ctx->ecache.valid = false;
     const int A = ctx->Amax;
     // per-pattern checks, the last alleles and the successor range check run on the device after the upload (model_check_kernel,
     // succ16_kernel): host loops over millions of patterns would cost more than the copies

@@ -115,8 +115,11 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
     DevBuf<EstepScratch> &d_edesc = ctx->d_edesc;
     CK(d_eflags.ensure(4));
 
+    const bool reuse = ctx->ecache.valid && ctx->ecache.first == first && ctx->ecache.count == count && ctx->ecache.flags == flags &&
+                       !getenv("HMC_B200_NO_ESTEP_CACHE");
     auto after = [&](const FwdParams &fp, int n_wave, const std::vector<int> &, int &launches) -> int {
         const int L = ctx->L;
+        if (!reuse) {
         // K3
         BackParams bp = {};
         bp.panel = fp.panel; bp.model = fp.model; bp.arena = ctx->d_arena.p; bp.loci = ctx->d_loci.p; bp.wave = ctx->d_wave.p; bp.status = ctx->d_status.p;
@@ -127,6 +130,7 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         ++launches;
+        }
         // K4: scratch sized from the largest live-state set of this wave
         long long hc[8];
         CK(cudaMemcpyAsync(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -178,7 +182,7 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
             CK(cudaMemcpyAsync(eflags, d_eflags.p, sizeof eflags, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             float ms = 0;
-            cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); if (attempt == 0) ctx->kernel_ms[2] += ms;
+            if (!reuse) { cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); if (attempt == 0) ctx->kernel_ms[2] += ms; }
             cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->kernel_ms[3] += ms;
             if (eflags[2] == 0) return HMC_OK;
             if (eflags[2] == 2) return ctx->fail(HMC_ERR_LIMIT, "candidate trie deeper than %d", ESTEP_MAX_DEPTH);
@@ -189,6 +193,20 @@ static int estimate_counts_impl(hmc_ctx *ctx, int first, int count, unsigned fla
         }
         return ctx->fail(HMC_ERR_LIMIT, "E-step entry stack overflow");
     };
+    if (reuse) {
+        // same individuals, same model, trellis still in the arena: only the candidate list changed (the later E-passes of an M-step)
+        const std::vector<int> none;
+        int launches = 0;
+        memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
+        CK(cudaMemsetAsync(ctx->d_counters.p + 7, 0, sizeof(long long), ctx->stream));
+        rc = after(ctx->ecache.fp, ctx->ecache.n_wave, none, launches);
+        if (rc) { ctx->ecache.valid = false; return rc; }
+        long long entries = 0;
+        CK(cudaMemcpy(&entries, ctx->d_counters.p + 7, sizeof entries, cudaMemcpyDeviceToHost));
+        memcpy(ctx->counters, ctx->ecache.counters, sizeof ctx->counters);
+        ctx->counters[HMC_CNT_ESTEP_ENTRIES] = entries; ctx->counters[HMC_CNT_LAUNCHES] = launches;
+        return HMC_OK;
+    }
     return run_waves(ctx, first, count, 1, flags, 1, after);
 }
 

@@ -51,6 +51,7 @@ static int flat_build_pool(hmc_ctx *ctx, FlatPool &fp, int n, int K)
 static int run_flat(hmc_ctx *ctx, FlatPool &fp, int first, int count, int K, unsigned flags)
 {
     const int L = ctx->L, kmax = kmax_for(K);
+    ctx->ecache.valid = false;
     int rc = ensure_arena(ctx);
     if (rc) return rc;
     rc = flat_build_pool(ctx, fp, count, K);

@@ -278,6 +278,7 @@ static int run_build_automaton(hmc_ctx *ctx, MinePool &mp, AutPool &ap, int head
     // model arrays of the context
     if (mp.handed_over) return ctx->fail(HMC_ERR_INVALID, "hmc_build_automaton: this pattern list already became the model");
     ctx->have_model = false;
+    ctx->ecache.valid = false;
     if ((size_t) P * 28 + (size_t) mp.n_alleles > ((size_t) 2 << 30)) {
         // large lists: their device arrays BECOME the model's (swap, no copy, nothing held twice): start, transition probability,
         // frequency, allele strings; fetch / map are over for this list

@@ -111,3 +111,51 @@ def test_estep_scaled_matches_unscaled():
     f1, pf1 = dev.estimate_counts(m["start"], m["al_off"], m["al"], r1["pg"], r1["exp"], flags=FLAG_SCALED)
     assert rel_close(f0, f1) and rel_close(pf0, pf1)
     dev.close()
+
+
+def test_later_epasses_reuse_the_trellis(monkeypatch):
+    """The E-passes of one M-step share model and individuals: after the first pass the E-step trellis (alpha, beta, links) stays
+    in the arena and the next hmc_estimate_counts calls go straight to K4.  Same counts as a from-scratch pass; the reuse ends
+    with any call that changes the model, the panel or the arena."""
+    g = make_panel(60, 50, founders=6, missing=0.04, seed=61)
+    o = Oracle(g)
+    o.find_patterns()
+    o.resolve_all()
+    dev, m = setup(g, o)
+    r = dev.resolve_all(K=1, haps=False)
+    P = m["P"]
+    # pass 1: all patterns; pass 2: a different candidate list (every other pattern)
+    f1, pf1 = dev.estimate_counts(m["start"], m["al_off"], m["al"], r["pg"])
+    k1, c1 = dev.kernel_ms(), dev.counters()
+    assert k1["forward"] > 0 and k1["backward"] > 0 and c1["estep_entries"] > 0
+    keep = np.arange(0, P, 2)
+    lens = (m["al_off"][1:] - m["al_off"][:-1])[keep]
+    off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    al2 = np.concatenate([m["al"][m["al_off"][i]:m["al_off"][i + 1]] for i in keep]).astype(np.int8)
+    st2 = np.ascontiguousarray(m["start"][keep])
+    f2, pf2 = dev.estimate_counts(st2, off2, al2, r["pg"])
+    k2, c2 = dev.kernel_ms(), dev.counters()
+    assert k2["forward"] == 0 and k2["backward"] == 0 and k2["estep"] > 0          # reused
+    assert c2["steps"] == c1["steps"] and c2["states"] == c1["states"] and 0 < c2["estep_entries"] <= c1["estep_entries"]
+    monkeypatch.setenv("HMC_B200_NO_ESTEP_CACHE", "1")
+    f3, pf3 = dev.estimate_counts(st2, off2, al2, r["pg"])
+    assert dev.kernel_ms()["forward"] > 0
+    assert rel_close(f2, f3) and rel_close(pf2, pf3)
+    monkeypatch.delenv("HMC_B200_NO_ESTEP_CACHE")
+    # a pattern's own count does not depend on which other candidates are in the list
+    assert rel_close(f2, f1[keep])
+    # the oracle agrees
+    ef, epf, _ = o.estep(st2, off2, al2)
+    fn, pfn, _ = dev.normalise_counts(f2, pf2, 60)
+    assert rel_close(fn, ef) and rel_close(pfn, epf)
+    # model upload ends the reuse
+    dev.set_model(m)
+    dev.estimate_counts(st2, off2, al2, r["pg"])
+    assert dev.kernel_ms()["forward"] > 0
+    # and so does a resolve pass
+    dev.estimate_counts(st2, off2, al2, r["pg"])
+    assert dev.kernel_ms()["forward"] == 0
+    dev.resolve_all(K=1, haps=False)
+    dev.estimate_counts(st2, off2, al2, r["pg"])
+    assert dev.kernel_ms()["forward"] > 0
+    dev.close()
