@@ -110,6 +110,12 @@ def test_estep_scaled_matches_unscaled():
     assert r1["exp"].max() > 0
     f1, pf1 = dev.estimate_counts(m["start"], m["al_off"], m["al"], r1["pg"], r1["exp"], flags=FLAG_SCALED)
     assert rel_close(f0, f1) and rel_close(pf0, pf1)
+    # a second scaled pass reuses the trellis together with its forward / backward exponent tables
+    f2, pf2 = dev.estimate_counts(m["start"], m["al_off"], m["al"], r1["pg"], r1["exp"], flags=FLAG_SCALED)
+    assert dev.kernel_ms()["forward"] == 0 and rel_close(f1, f2) and rel_close(pf1, pf2)
+    # ... but not across a change of the scaling flag
+    f3, pf3 = dev.estimate_counts(m["start"], m["al_off"], m["al"], r0["pg"])
+    assert dev.kernel_ms()["forward"] > 0 and rel_close(f0, f3)
     dev.close()
 
 
