@@ -13,8 +13,6 @@
 
 #include "common.cuh"
 #include "forward.cuh"
-#include "forward_warp.cuh"
-#include "forward_flat.cuh"
 #include "mine.cuh"
 #include "automaton.cuh"
 #include "compare.cuh"
@@ -23,10 +21,14 @@
 #include <climits>
 #include <thread>
 #include <atomic>
-#include "traceback.cuh"
+#include "kbest.cuh"
 #include "estep.cuh"
 
 using namespace hmc;
+
+#ifndef FWD_MINB_128
+#define FWD_MINB_128 6
+#endif
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -51,7 +53,7 @@ struct DevBuf {
 };
 
 struct ScratchPool {
-    int slots = 0, K = 0;
+    int slots = 0;
     int hcap = 0, ccap = 0, scap = 0;
     DevBuf<unsigned char> mem;
     DevBuf<Scratch> desc;
@@ -111,6 +113,9 @@ struct hmc_ctx {
     DevBuf<LocusRec> d_loci;
     DevBuf<int> d_wave, d_status, d_final_exp, d_locus_exp;
     DevBuf<long long> d_cycles;
+    DevBuf<u64> d_kb_eoff;
+    DevBuf<u32> d_kb_chain, d_kb_stack;
+    int64_t kb_work[3] = {};
     std::vector<int> h_wave;                 // last wave (for hmc_get_trellis)
     int last_K = 0, last_estep = 0;
     ScratchPool pool, big_pool;
@@ -129,7 +134,6 @@ struct hmc_ctx {
     DevBuf<EstepScratch> d_edesc;
     DevBuf<int> d_pgexp;
 
-    struct FlatPool *flat = nullptr;
     int64_t counters[HMC_CNT_N] = {};
     float kernel_ms[4] = {};
 
@@ -230,11 +234,11 @@ __global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NT, int CC, int CL, int KMAX, int MINB = 512 / NT>
+template <int NT, int CC, int MINB>
 static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
 {
-    auto kern = forward_kernel<NT, CC, CL, KMAX, MINB>;
-    const size_t smem = sizeof(FwdSmem<NT, CC, CL, KMAX>);
+    auto kern = forward_kernel<NT, CC, MINB>;
+    const size_t smem = sizeof(FwdSmem<NT, CC>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, NT, smem);
@@ -242,94 +246,24 @@ static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-template <int NT, int CC, int CL>
-static cudaError_t launch_forward_k(int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
-{
-    switch (kmax) {
-        case 1: return launch_forward_t<NT, CC, CL, 1>(p, grid, st, occ);
-        case 4: return launch_forward_t<NT, CC, CL, 4>(p, grid, st, occ);
-        case 10: return launch_forward_t<NT, CC, CL, 10>(p, grid, st, occ);
-        case 16: return launch_forward_t<NT, CC, CL, 16>(p, grid, st, occ);
-        default: return launch_forward_t<NT, CC, CL / 2, 32>(p, grid, st, occ);
-    }
-}
-
-template <int CS, int CL, int KMAX>
-static cudaError_t launch_warp_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
-{
-    auto kern = forward_warp_kernel<CS, CL, KMAX>;
-    const size_t smem = sizeof(WarpSmem<CS, CL, KMAX>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, 32, smem);
-    kern<<<grid, 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_warp(int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
-{
-    switch (kmax) {
-        case 1: return launch_warp_t<256, 256, 1>(p, grid, st, occ);
-        case 4: return launch_warp_t<256, 128, 4>(p, grid, st, occ);
-        case 10: return launch_warp_t<256, 64, 10>(p, grid, st, occ);
-        case 16: return launch_warp_t<256, 48, 16>(p, grid, st, occ);
-        default: return launch_warp_t<256, 32, 32>(p, grid, st, occ);
-    }
-}
-
-static cudaError_t launch_forward(int nt, int kmax, const FwdParams &p, int grid, cudaStream_t st, int *occ)
+// threads per individual -> kernel configuration (candidate slots of the shared-memory fast path, resident CTAs per SM)
+static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStream_t st, int *occ)
 {
     switch (nt) {
-        case 32: return launch_warp(kmax, p, grid, st, occ);
-        case 33: return launch_forward_k<32, 128, 64>(kmax, p, grid, st, occ);
-        case 64:
-            switch (kmax) {
-                case 1: return launch_forward_t<64, 128, 64, 1, 8>(p, grid, st, occ);
-                case 4: return launch_forward_t<64, 128, 32, 4, 8>(p, grid, st, occ);
-                case 10: return launch_forward_t<64, 128, 16, 10, 8>(p, grid, st, occ);
-                case 16: return launch_forward_t<64, 128, 12, 16, 8>(p, grid, st, occ);
-                default: return launch_forward_t<64, 128, 8, 32, 8>(p, grid, st, occ);
-            }
-        case 128:
-            // Measured on C2 (profiles/README.md): small shared-memory footprints win -- what is not carved out as shared memory is L1
-            // for the successor gathers, the spilled hash / segment arrays and the K-best lists -- and 4-5 CTAs per SM beat larger
-            // fast-path capacities.
-            switch (kmax) {
-                case 1: return launch_forward_t<128, 256, 64, 1, 5>(p, grid, st, occ);
-                case 4: return launch_forward_t<128, 256, 64, 4, 4>(p, grid, st, occ);
-                case 10: return launch_forward_t<128, 256, 32, 10, 4>(p, grid, st, occ);
-                case 16: return launch_forward_t<128, 256, 24, 16, 4>(p, grid, st, occ);
-                default: return launch_forward_t<128, 256, 12, 32, 4>(p, grid, st, occ);
-            }
-        default: return launch_forward_k<256, 1024, 256>(kmax, p, grid, st, occ);
+        case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
+        case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
+        case 256: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
+        default: return launch_forward_t<128, 256, FWD_MINB_128>(p, grid, st, occ);
     }
 }
 
-static int kmax_for(int K) { return K <= 1 ? 1 : K <= 4 ? 4 : K <= 10 ? 10 : K <= 16 ? 16 : 32; }
-
-static cudaError_t launch_traceback(int kmax, const TraceParams &p, cudaStream_t st)
+// size / (re)build a scratch pool: one Scratch per persistent CTA.  The hash arrays start all-empty and every kernel leaves them so.
+static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int scap, int ccap, int hcap)
 {
-    const int wpb = 4;
-    const int grid = (p.n_wave + wpb - 1) / wpb;
-    switch (kmax) {
-        case 1: traceback_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 4: traceback_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 10: traceback_kernel<10><<<grid, wpb * 32, 0, st>>>(p); break;
-        case 16: traceback_kernel<16><<<grid, wpb * 32, 0, st>>>(p); break;
-        default: traceback_kernel<32><<<grid, wpb * 32, 0, st>>>(p); break;
-    }
-    return cudaGetLastError();
-}
-
-// size / (re)build a scratch pool: one Scratch per persistent CTA
-static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap, int ccap, int hcap)
-{
-    if (pl.slots >= slots && pl.K >= K && pl.scap == scap && pl.ccap == ccap && pl.hcap == hcap) return HMC_OK;
+    if (pl.slots >= slots && pl.scap == scap && pl.ccap == ccap && pl.hcap == hcap) return HMC_OK;
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-    const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_s = al((size_t) (scap + 1) * 4);
-    const size_t b_like = al((size_t) scap * K * 8), b_meta = al((size_t) scap * 8);
-    const size_t b_obp = al((size_t) scap * K * 4);
-    const size_t per = 2 * b_keys + 2 * b_u32 + 2 * b_c + 3 * b_s + 2 * b_like + 3 * b_meta + b_obp;
+    const size_t b_keys = al((size_t) hcap * 8), b_u32 = al((size_t) hcap * 4), b_c = al((size_t) ccap * 4), b_m = al((size_t) scap * 8);
+    const size_t per = 2 * b_keys + 3 * b_u32 + 2 * b_c + b_m;
     CK(pl.mem.ensure(per * slots));
     CK(pl.desc.ensure(slots));
     std::vector<Scratch> h(slots);
@@ -341,22 +275,17 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int K, int scap,
         s.tpv = (double *) b; b += b_keys;
         s.ord = (u32 *) b; b += b_u32;
         s.cnt = (u32 *) b; b += b_u32;
-        s.nidx = nullptr;
+        s.soff = (u32 *) b; b += b_u32;
         s.cand = (int *) b; b += b_c;
-        s.arr = (int *) b; b += b_c;
-        s.aoff = (int *) b; b += b_s;
-        s.slot_of = (int *) b; b += b_s;
-        s.order = (int *) b; b += b_s;
-        s.like[0] = (double *) b; b += b_like;
-        s.like[1] = (double *) b; b += b_like;
-        s.meta[0] = (u64 *) b; b += b_meta;
-        s.meta[1] = (u64 *) b; b += b_meta;
-        s.otp = (double *) b; b += b_meta;
-        s.obp = (u32 *) b; b += b_obp;
+        s.sarr = (int *) b; b += b_c;
+        s.mlist = (int2 *) b; b += b_m;
+        CK(cudaMemsetAsync(s.keys, 0xFF, (size_t) hcap * 8, ctx->stream));
+        CK(cudaMemsetAsync(s.ord, 0xFF, (size_t) hcap * 4, ctx->stream));
+        CK(cudaMemsetAsync(s.cnt, 0, (size_t) hcap * 4, ctx->stream));
     }
     CK(cudaMemcpyAsync(pl.desc.p, h.data(), sizeof(Scratch) * slots, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    pl.slots = slots; pl.K = K; pl.scap = scap; pl.ccap = ccap; pl.hcap = hcap;
+    pl.slots = slots; pl.scap = scap; pl.ccap = ccap; pl.hcap = hcap;
     return HMC_OK;
 }
 
@@ -380,7 +309,7 @@ static int pick_threads(const hmc_ctx *ctx)
     const char *env = getenv("HMC_B200_THREADS");
     int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
     if (nt == 0) nt = 128;
-    if (nt != 32 && nt != 33 && nt != 64 && nt != 128 && nt != 256) nt = 128;    // (1 = level-synchronous path; its fallback uses 128)
+    if (nt != 32 && nt != 64 && nt != 128 && nt != 256) nt = 128;
     return nt;
 }
 
@@ -398,17 +327,16 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     if (rc) return rc;
     CK(ctx->d_cursor.ensure(1));
     CK(ctx->d_flags.ensure(2));
-    CK(ctx->d_counters.ensure(24));
+    CK(ctx->d_counters.ensure(32));
     ctx->ecache.valid = false;
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 24 * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(long long), ctx->stream));
     memset(ctx->counters, 0, sizeof ctx->counters);
     memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
 
     const int nt = pick_threads(ctx);
-    const int kmax = kmax_for(K);
     int occ = 1;
     FwdParams fp = {};
-    CK(launch_forward(nt, kmax, fp, 0, ctx->stream, &occ));
+    CK(launch_forward(nt, fp, 0, ctx->stream, &occ));
     if (occ < 1) occ = 1;
     const int max_slots = ctx->sms * occ;
 
@@ -419,7 +347,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     CK(ctx->d_wave.ensure(wave_cap));
     CK(ctx->d_status.ensure(wave_cap));
     CK(ctx->d_final_exp.ensure(wave_cap));
-    if (estep && (flags & HMC_FLAG_SCALED)) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * (L + 1)));
+    if (flags & HMC_FLAG_SCALED) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * (L + 1)));
 
     // pending individuals, heaviest first
     std::vector<int> pending;
@@ -429,14 +357,15 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     std::vector<int> h_status;
     bool big_mode = false;
     int waves = 0, launches = 0;
+    double fwd_share = 0.9;     // resolve mode: the part of the arena the forward kernel may fill; the rest is left to the K-best kernel's lists / nodes
 
     while (!pending.empty() || (!big_mode && !big.empty())) {
         if (pending.empty()) { big_mode = true; pending.swap(big); }
         const int n_wave = (int) std::min<size_t>(pending.size(), (size_t) wave_cap);
         ScratchPool &pl = big_mode ? ctx->big_pool : ctx->pool;
         int slots;
-        if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, K, 1 << 20, 1 << 22, 1 << 23); }
-        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, K, 1 << 16, 1 << 18, 1 << 19); }
+        if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, 1 << 20, 1 << 22, 1 << 23); }
+        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, 1 << 16, 1 << 18, 1 << 19); }
         if (rc) return rc;
         ctx->h_wave.assign(pending.begin(), pending.begin() + n_wave);
         CK(cudaMemcpyAsync(ctx->d_wave.p, ctx->h_wave.data(), sizeof(int) * n_wave, cudaMemcpyHostToDevice, ctx->stream));
@@ -447,27 +376,38 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         fp.panel.N = ctx->N; fp.panel.L = L; fp.panel.Amax = ctx->Amax; fp.panel.bits = ctx->bits; fp.panel.words = ctx->words;
         fp.panel.packed = ctx->d_packed.p; fp.panel.linfo = ctx->d_linfo.p; fp.panel.order = ctx->d_order.p;
         fp.model = ctx->dm;
-        fp.arena.base = ctx->d_arena.p; fp.arena.capacity = (long long) ctx->d_arena.n; fp.arena.cursor = ctx->d_cursor.p; fp.arena.exhausted = ctx->d_flags.p;
+        fp.arena.base = ctx->d_arena.p; fp.arena.capacity = estep ? (long long) ctx->d_arena.n : (long long) ((double) ctx->d_arena.n * fwd_share);
+        fp.arena.cursor = ctx->d_cursor.p; fp.arena.exhausted = ctx->d_flags.p;
         fp.scratch = pl.desc.p;
         fp.loci = ctx->d_loci.p; fp.wave = ctx->d_wave.p; fp.n_wave = n_wave; fp.K = K; fp.estep = estep;
         fp.scaled = (flags & HMC_FLAG_SCALED) ? 1 : 0;
         fp.status = ctx->d_status.p; fp.final_exp = ctx->d_final_exp.p;
-        fp.locus_exp = (estep && fp.scaled) ? ctx->d_locus_exp.p : nullptr;
+        fp.locus_exp = fp.scaled ? ctx->d_locus_exp.p : nullptr;
         fp.queue = ctx->d_flags.p + 1; fp.counters = ctx->d_counters.p;
         fp.ind_cycles = nullptr;
-        if (getenv("HMC_B200_DEBUG_CYCLES")) { CK(ctx->d_cycles.ensure(wave_cap)); CK(cudaMemsetAsync(ctx->d_cycles.p, 0, sizeof(long long) * n_wave, ctx->stream)); fp.ind_cycles = ctx->d_cycles.p; }
+        if (getenv("HMC_B200_DEBUG_CYCLES")) { CK(ctx->d_cycles.ensure((size_t) wave_cap * 8)); CK(cudaMemsetAsync(ctx->d_cycles.p, 0, sizeof(long long) * 8 * n_wave, ctx->stream)); fp.ind_cycles = ctx->d_cycles.p; }
 
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        CK(launch_forward(nt, kmax, fp, slots, ctx->stream, nullptr));
+        CK(launch_forward(nt, fp, slots, ctx->stream, nullptr));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ++launches;
         if (!estep) {
-            TraceParams tp = {};
-            tp.panel = fp.panel; tp.model = fp.model; tp.arena = ctx->d_arena.p; tp.loci = ctx->d_loci.p; tp.wave = ctx->d_wave.p;
-            tp.status = ctx->d_status.p; tp.final_exp = ctx->d_final_exp.p; tp.n_wave = n_wave; tp.K = K; tp.first = first;
-            tp.pg = ctx->d_pg.p; tp.cov = ctx->d_cov.p; tp.prior = ctx->d_prior.p; tp.post = ctx->d_post.p; tp.exp2 = ctx->d_exp.p; tp.nres = ctx->d_nres.p;
-            tp.haps = ctx->d_haps.p;
-            CK(launch_traceback(kmax, tp, ctx->stream));
+            // K2: lazy K-best enumeration + traceback, one warp per individual (persistent warps)
+            const int kb_warps = std::min(n_wave, ctx->sms * 16);
+            const int kb_grid = (kb_warps + KB_WARPS - 1) / KB_WARPS;
+            const size_t nw = (size_t) kb_grid * KB_WARPS;
+            CK(ctx->d_kb_eoff.ensure(nw * (L + 2))); CK(ctx->d_kb_chain.ensure(nw * (L + 2))); CK(ctx->d_kb_stack.ensure(nw * (L + 40)));
+            CK(cudaMemsetAsync(ctx->d_flags.p + 1, 0, sizeof(int), ctx->stream));        // the work queue is reused
+            KbParams kp = {};
+            kp.panel = fp.panel; kp.model = fp.model; kp.arena = ctx->d_arena.p; kp.capacity = (long long) ctx->d_arena.n; kp.cursor = ctx->d_cursor.p;
+            kp.loci = ctx->d_loci.p; kp.wave = ctx->d_wave.p; kp.status = ctx->d_status.p; kp.final_exp = ctx->d_final_exp.p; kp.locus_exp = fp.locus_exp;
+            kp.n_wave = n_wave; kp.K = K; kp.first = first;
+            kp.eoff = ctx->d_kb_eoff.p; kp.chain = ctx->d_kb_chain.p; kp.stack = ctx->d_kb_stack.p; kp.stack_stride = L + 40;
+            kp.queue = ctx->d_flags.p + 1; kp.work = (unsigned long long *) (ctx->d_counters.p + 24);
+            kp.pg = ctx->d_pg.p; kp.cov = ctx->d_cov.p; kp.prior = ctx->d_prior.p; kp.post = ctx->d_post.p; kp.exp2 = ctx->d_exp.p; kp.nres = ctx->d_nres.p;
+            kp.haps = ctx->d_haps.p;
+            kbest_kernel<<<kb_grid, KB_WARPS * 32, 0, ctx->stream>>>(kp);
+            CK(cudaGetLastError());
             ++launches;
         }
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -481,11 +421,12 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         if (rc) return rc;
 
         std::vector<int> again;
-        int done = 0;
+        int done = 0, kb_fail = 0;
         for (int q = 0; q < n_wave; ++q) {
             switch (h_status[q]) {
                 case ST_DONE: ++done; break;
                 case ST_NOMEM: case ST_PENDING: again.push_back(ctx->h_wave[q]); break;
+                case ST_NOMEM_KBEST: again.push_back(ctx->h_wave[q]); ++kb_fail; break;
                 case ST_TOO_BIG:
                     if (big_mode) return ctx->fail(HMC_ERR_LIMIT, "individual %d exceeds the per-locus state capacity", ctx->h_wave[q]);
                     big.push_back(ctx->h_wave[q]);
@@ -495,12 +436,14 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             }
         }
         ++waves;
-        if (done == 0 && big.empty() && !again.empty() && (int) again.size() == n_wave)
+        // every individual of the wave ran out of arena: the first one had it to itself (the queue hands them out in order), so it can never fit
+        if (kb_fail) fwd_share *= 0.5;      // the K-best kernel ran out of room behind the trellis: leave it more in the next wave
+        if (done == 0 && !again.empty() && (int) again.size() == n_wave && (kb_fail == 0 || fwd_share < 0.01))
             return ctx->fail(HMC_ERR_NOMEM, "trellis arena (%zu MB) cannot hold a single individual", ctx->d_arena.n * 8 >> 20);
         pending.erase(pending.begin(), pending.begin() + n_wave);
         pending.insert(pending.begin(), again.begin(), again.end());
     }
-    long long hc[24];
+    long long hc[32];
     CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
     if (getenv("HMC_B200_PRINT_PASSES"))
         for (int b = 8; b < 24; b += 8)
@@ -509,6 +452,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
+    ctx->kb_work[0] = hc[24]; ctx->kb_work[1] = hc[25]; ctx->kb_work[2] = hc[26];
     ctx->last_K = K; ctx->last_estep = estep;
     if (estep && waves == 1) {
         ctx->ecache.first = first; ctx->ecache.count = count; ctx->ecache.flags = flags; ctx->ecache.fp = fp; ctx->ecache.n_wave = fp.n_wave;
@@ -518,7 +462,6 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     return HMC_OK;
 }
 
-#include "flat_capi.inl"
 #include "mine_capi.inl"
 
 // ---------------------------------------------------------------------------------------------
@@ -558,7 +501,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
     ctx->trie.release(); ctx->d_bexp.release(); ctx->d_eflags.release(); ctx->d_escr.release(); ctx->d_edesc.release(); ctx->d_cycles.release();
-    if (ctx->flat) { ctx->flat->release(); delete ctx->flat; }
+    ctx->d_kb_eoff.release(); ctx->d_kb_chain.release(); ctx->d_kb_stack.release();
     if (ctx->mine) { ctx->mine->release(); delete ctx->mine; }
     if (ctx->aut) { ctx->aut->release(); delete ctx->aut; }
     ctx->d_af.release(); ctx->d_best_packed.release(); ctx->d_cmp_real.release(); ctx->d_cmp_infer.release(); ctx->d_cmp_out.release();
@@ -575,6 +518,8 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     if (Amax < 1 || Amax > HMC_MAX_ALLELES) return ctx->fail(HMC_ERR_LIMIT, "Amax %d outside [1,%d]", Amax, HMC_MAX_ALLELES);
     CK(cudaSetDevice(ctx->device));
     ctx->ecache.valid = false;
+    ctx->have_model = false;        // the automaton tables (successor stride, head table) belong to the previous panel's allele tables
+    ctx->r_count = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax;
     ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
     const int per = 32 / (2 * ctx->bits);
@@ -627,6 +572,8 @@ int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const u
     if (bits != (Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8))) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel_packed: %d bits per allele do not match Amax %d", bits, Amax);
     CK(cudaSetDevice(ctx->device));
     ctx->ecache.valid = false;
+    ctx->have_model = false;
+    ctx->r_count = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
     const int per = 32 / (2 * bits);
     ctx->words = (L + per - 1) / per;
@@ -687,7 +634,11 @@ int hmc_set_model(hmc_ctx *ctx, int P, int head_len, const int32_t *start, const
         if (id < 0 || id >= P || start[id] != 0 || end[id] != head_len || al_off[id] < 0 || al_off[id] + head_len > al_off[P])
             return ctx->fail(HMC_ERR_INVALID, "head %d is not a start-0 pattern of length head_len", id);
         long long code = 0;
-        for (int j = 0; j < head_len; ++j) code += (long long) alleles[al_off[id] + j] * stride[j];
+        for (int j = 0; j < head_len; ++j) {
+            const int a = alleles[al_off[id] + j];
+            if (a < 0 || a >= std::max(1, ctx->h_nall[j])) return ctx->fail(HMC_ERR_INVALID, "head %d: allele %d at locus %d outside [0,%d)", id, a, j, ctx->h_nall[j]);
+            code += (long long) a * stride[j];
+        }
         lut[(size_t) code] = id;
     }
     CK(ctx->d_succ16.ensure((size_t) P * A));
@@ -740,19 +691,11 @@ int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned f
     CK(ctx->d_pg.ensure(count)); CK(ctx->d_cov.ensure(count)); CK(ctx->d_exp.ensure(count)); CK(ctx->d_nres.ensure(count));
     CK(ctx->d_prior.ensure((size_t) count * K)); CK(ctx->d_post.ensure((size_t) count * K));
     CK(ctx->d_haps.ensure((size_t) count * K * 2 * L));
-    ctx->r_first = first; ctx->r_count = count; ctx->r_K = K;
-    {   // level-synchronous path (threads == 1 or HMC_B200_FLAT=1); falls back to the per-individual kernel when a capacity is exceeded
-        const char *env = getenv("HMC_B200_FLAT");
-        if (ctx->threads_opt == 1 || (env && atoi(env) == 1 && ctx->threads_opt == 0)) {
-            if (ctx->N <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_set_panel has not been called");
-            if (!ctx->have_model) return ctx->fail(HMC_ERR_INVALID, "hmc_set_model has not been called");
-            if (first < 0 || first + count > ctx->N) return ctx->fail(HMC_ERR_INVALID, "individual range [%d,%d) outside the panel", first, first + count);
-            if (!ctx->flat) ctx->flat = new FlatPool;
-            const int rc = run_flat(ctx, *ctx->flat, first, count, K, flags);
-            if (rc <= 0) return rc;
-        }
-    }
-    return run_waves(ctx, first, count, K, flags, 0, [](const FwdParams &, int, const std::vector<int> &, int &) { return 0; });
+    ctx->r_count = 0;           // fetch / compare / mine_resolved must not see partial results of a failed call
+    ctx->r_first = first; ctx->r_K = K;
+    const int rc = run_waves(ctx, first, count, K, flags, 0, [](const FwdParams &, int, const std::vector<int> &, int &) { return 0; });
+    if (rc == HMC_OK) ctx->r_count = count;
+    return rc;
 }
 
 int hmc_fetch_results(hmc_ctx *ctx, double *out_pg, int32_t *out_exp, double *out_cov, int32_t *out_nres, double *out_prior, double *out_post,
@@ -986,12 +929,13 @@ int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N])
     return HMC_OK;
 }
 
-// diagnostics (HMC_B200_DEBUG_CYCLES=1): SM cycles per individual of the last wave, in wave order; returns the count
+// diagnostics (HMC_B200_DEBUG_CYCLES=1): per individual of the last wave, in wave order, 8 values {SM cycles, states, max states,
+// arrivals, spill steps, start ns, end ns, CTA}; `out` holds 8 * cap values; returns the count
 int hmc_debug_cycles(hmc_ctx *ctx, long long *out, int *inds, int cap)
 {
     if (!ctx || !ctx->d_cycles.p) return 0;
     const int n = std::min<int>(cap, (int) ctx->h_wave.size());
-    cudaMemcpy(out, ctx->d_cycles.p, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, ctx->d_cycles.p, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
     for (int i = 0; i < n; ++i) inds[i] = ctx->h_wave[i];
     return n;
 }
@@ -1020,7 +964,7 @@ int64_t hmc_get_trellis(hmc_ctx *ctx, int individual, int32_t *counts, int64_t c
         counts[l] = S;
         if (S <= 0) continue;
         if (tot + S > capacity) return ctx->fail(HMC_ERR_INVALID, "trellis capacity too small");
-        const BlockLayout b = block_layout(S, ctx->last_K, ctx->last_estep);
+        const BlockLayout b = block_layout(S, 0, ctx->last_estep);
         const u64 *blk = ctx->d_arena.p + rec[l].off;
         cudaError_t e = cudaSuccess;
         if (ida) e = cudaMemcpy(ida + tot, blk + b.ida, sizeof(int) * S, cudaMemcpyDeviceToHost);

@@ -22,8 +22,14 @@ constexpr u32 BP_REV = 0x20000000u;
 constexpr int BP_PRED_BITS = 24;
 constexpr int MAX_STATES_PER_LOCUS = 1 << BP_PRED_BITS;
 
+// arrival word of the per-state arrival lists (resolve mode): bits 0..23 predecessor state index,
+// 30 the step's allele pair was heterozygous (HaploPair.cpp:53,77), 31 reversed
+constexpr u32 ARR_HET = 0x40000000u;
+constexpr u32 ARR_REV = 0x80000000u;
+constexpr u32 ARR_PRED_MASK = (1u << BP_PRED_BITS) - 1u;
+
 // individual status written by the forward kernel
-enum : int { ST_PENDING = 0, ST_DONE = 1, ST_NOMEM = 2, ST_TOO_BIG = 3, ST_NO_HEAD = 4 };
+enum : int { ST_PENDING = 0, ST_DONE = 1, ST_NOMEM = 2, ST_TOO_BIG = 3, ST_NO_HEAD = 4, ST_NOMEM_KBEST = 5 };
 
 // The panel on the device: genotypes bit-packed per individual x locus (K0).
 struct DevPanel {
@@ -68,19 +74,14 @@ struct Arena {
 };
 
 // Per-CTA (persistent slot) spill scratch in global memory, used when a step does not fit the
-// shared-memory fast path, plus the K-best likelihood ping-pong.
+// shared-memory fast path.  The hash arrays are all-empty between steps (slots are reset by their owners).
 struct Scratch {
     int hcap, ccap, scap;       // hash slots (power of two), candidate slots, states
     u64 *keys;                  // [hcap]
     double *tpv;                // [hcap] transition-probability product of the slot's state
-    double *otp;                // [scap] warp kernel: transition probability of spilled output states
-    u32 *obp;                   // [scap*K] warp kernel: back-pointer words of spilled output states
-    u32 *ord, *cnt, *nidx;      // [hcap]
-    int *cand, *arr;            // [ccap]
-    int *aoff, *slot_of;        // [scap+1], [scap]
-    int *order;                 // [scap] pass-E visiting order (light states first)
-    double *like[2];            // [scap*K]
-    u64 *meta[2];               // [scap]  (links | hom mask << 8)
+    u32 *ord, *cnt, *soff;      // [hcap] smallest candidate ordinal -> state index; arrivals; arrival-segment offset
+    int *cand, *sarr;           // [ccap] slot | rev << 30 of every candidate; arrival ordinals grouped by state
+    int2 *mlist;                // [scap] {state index, slot} of the states with more than one arrival
 };
 
 struct FwdParams {
@@ -96,28 +97,37 @@ struct FwdParams {
     int scaled;
     int *status;                // [n_wave]
     int *final_exp;             // [n_wave]
-    int *locus_exp;             // [n_wave][L+1] cumulative exponent (scaled mode, E-step) or null
+    int *locus_exp;             // [n_wave][L+1] cumulative exponent (scaled mode) or null
     int *queue;                 // work-queue head
     long long *counters;        // steps, states, max_states, arrivals, -, spill steps
-    long long *ind_cycles;      // [n_wave] SM clock cycles spent on each individual (diagnostics) or null
+    long long *ind_cycles;      // [n_wave][8] per-individual diagnostics (cycles, states, ...) or null
 };
 
-// trellis state-block layout (units of 8 bytes) for S states
+// trellis state-block layout (units of 8 bytes) for S states with X arrivals.
+//   resolve mode: ida | idb | alpha | v1 (likelihood of the best path into the state) | last alleles | aoff[S+1] | arrival words[X]
+//   E-step mode:  ida | idb | alpha | last alleles | tp | beta        (X unused; forward links live in their own block)
 struct BlockLayout {
-    long long ida, idb, alpha, ab, bp, tp, beta, total;
+    long long ida, idb, alpha, v1, ab, aoff, arr, tp, beta, total;
 };
-__host__ __device__ inline BlockLayout block_layout(int S, int K, int estep)
+__host__ __device__ inline BlockLayout block_layout(int S, long long X, int estep)
 {
     BlockLayout b;
     long long s2 = (S + 1) / 2;     // S ints in 8-byte units
     b.ida = 0;
     b.idb = b.ida + s2;
     b.alpha = b.idb + s2;
-    b.ab = b.alpha + S;
-    long long o = b.ab + (S + 7) / 8;
-    b.bp = b.tp = b.beta = o;
-    if (estep) { b.tp = o; b.beta = o + S; o += 2LL * S; }
-    else { b.bp = o; o += ((long long) S * K + 1) / 2; }
+    long long o = b.alpha + S;
+    b.v1 = b.tp = b.beta = b.aoff = b.arr = o;
+    if (estep) {
+        b.ab = o; o += (S + 7) / 8;
+        b.tp = o; b.beta = o + S; o += 2LL * S;
+    }
+    else {
+        b.v1 = o; o += S;
+        b.ab = o; o += (S + 7) / 8;
+        b.aoff = o; o += (S + 2) / 2;
+        b.arr = o; o += (X + 1) / 2;
+    }
     b.total = o;
     return b;
 }

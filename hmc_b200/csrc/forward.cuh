@@ -1,22 +1,34 @@
-// K1 forward_resolve: the per-individual forward pass of HaploBuilder::resolve
+// K1 forward: the per-individual forward pass of HaploBuilder::resolve
 // (HaploBuilder.cpp:35-86 with initHeadList :153-224, extendAll/extend/addHaploPair :226-261 and the
 // HaploPair constructors / add, HaploPair.cpp:14-89).
 //
-// One CTA (NT threads, NT = 32 is one warp) owns one individual at a time and pulls individuals from
-// a work queue (persistent grid).  Per locus step the lanes are spread over the candidate slots
-// (predecessor state x ordered allele pair); the step is
-//   A   one 128-bit gather per haplotype from the successor table {successor id, its transition
-//       probability}, canonicalise (id_a <= id_b), insert into an open-addressing hash on (id_a,id_b);
-//       the slot remembers the smallest candidate ordinal that hit it
-//   B+C walk the candidates in ordinal order; the one whose ordinal equals the slot's minimum creates
-//       the state -> new states get exactly the reference's creation order; the same block scan
-//       yields the per-state arrival-segment offsets
-//   D   scatter arrivals into the per-state segments
-//   E   one lane per new state: arrivals in ordinal order -> alpha sum in the reference's order
-//       (no FMA), K-best merge of the predecessors' sorted link lists, het-locus rule, trellis write.
-// While a step fits (C <= CC candidate slots) the hash, candidate and segment arrays are in shared
-// memory and addressed as such (the step body is instantiated twice: shared / global spill scratch);
-// live states (ids, alpha) and, for small sets, their K-best lists are cached in shared memory too.
+// One CTA (NT threads) owns one individual at a time and pulls individuals from a work queue
+// (persistent grid).  What the kernel materialises per trellis index is the state set in the
+// reference's creation order with, per state, alpha (forward_likelihood), v1 = the likelihood of the
+// best link (the head of m_best_links) and the list of arrivals (predecessor, reversed, heterozygous
+// step) -- NOT the K-best link lists: those are a function of exactly this graph and are enumerated
+// lazily from the end of the trellis by the K2 kernel (kbest.cuh), which touches ~K states per index
+// instead of all of them.  alpha is accumulated over the arrivals in the reference's order with
+// explicit __dmul_rn / __dadd_rn, so it is bit-identical; v1 = max over arrivals of v1(pred) * tp is
+// order-free (rounding is monotone).
+//
+// Per locus step:
+//   A   lanes over the predecessor states: one 128-bit gather per (haplotype, allele) from the successor
+//       table {successor id, its transition probability}; per candidate (allele pair, orientation):
+//       canonicalise (id_a <= id_b), insert (id_a,id_b) into an open-addressing hash, atomicMin of the
+//       candidate ordinal, arrival count
+//   C   candidates in ordinal order, warps take 128-candidate tiles round robin and chain their
+//       (creators, arrivals) prefixes through a decoupled look-back ring in shared memory (no block
+//       barrier): the candidate whose ordinal equals its slot's minimum creates the state -> new states
+//       get exactly the reference's creation order; it writes ids / last alleles / arrival offset, and
+//       when it is the state's only arrival (about two thirds of the states) alpha, v1 and the arrival
+//       word as well, and frees its hash slot
+//   D   arrivals of the remaining (multi-arrival) states are scattered into per-state segments
+//   E   one lane per multi-arrival state: arrivals sorted by ordinal, alpha summed in that order,
+//       v1 = max, arrival words written, hash slot freed.
+// While a step fits (C <= CC candidate slots) the hash / candidate / segment arrays are in shared
+// memory (the step body is instantiated twice: shared / global spill scratch); the live states'
+// ids, alpha and v1 are cached in shared memory up to CC states.
 #pragma once
 
 #include <type_traits>
@@ -32,82 +44,50 @@ namespace hmc {
 #endif
 
 template <int NT>
-struct BlockScan {
-    // exclusive prefix sum over the block in thread order; total returned to every thread
-    __device__ static long long run(long long v, long long &total, long long *s_tmp)
-    {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        long long x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (NT == 32) { total = __shfl_sync(0xffffffffu, x, 31); return x - v; }
-        __syncthreads();            // protect s_tmp from the previous use
-        if (lane == 31) s_tmp[wid] = x;
-        __syncthreads();
-        long long base = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { long long t = s_tmp[w]; if (w < wid) base += t; tot += t; }
-        total = tot;
-        return base + x - v;
-    }
-};
-
-template <int NT>
 __device__ __forceinline__ void block_sync()
 {
     if (NT == 32) __syncwarp(); else __syncthreads();
 }
 
-// sorted-descending insert with static indexing (registers); slot KMAX-1 falls off the end.
-template <int KMAX>
-__device__ __forceinline__ void topk_insert(double (&bl)[KMAX], u32 (&bb)[KMAX], double v, u32 b)
-{
-#pragma unroll
-    for (int j = KMAX - 1; j >= 1; --j) {
-        const bool shift = v > bl[j - 1];
-        const bool place = !shift && (v > bl[j]);
-        if (shift) { bl[j] = bl[j - 1]; bb[j] = bb[j - 1]; }
-        else if (place) { bl[j] = v; bb[j] = b; }
-    }
-    if (v > bl[0]) { bl[0] = v; bb[0] = b; }
-}
-
-template <int NT, int CC, int CL, int KMAX>
+template <int NT, int CC>
 struct FwdSmem {
     static constexpr int HC = 2 * CC <= 256 ? 256 : 2 * CC <= 512 ? 512 : 2 * CC <= 1024 ? 1024 : 2 * CC <= 2048 ? 2048 : 4096;   // power of two >= 2 CC
     u64 keys[HC];
     double tpv[HC];
-    double alpha[2][CC];
-    double like[2][CL * KMAX];
-    u64 meta[2][CL];
+    double alpha[2][CC], v1[2][CC];
     long long ll[4];                // -, alloc result, chunk cursor, chunk end
-    long long tmp[8];               // scan scratch
-    u32 ord[HC], cnt[HC];
+    unsigned long long look[8];     // look-back ring of pass C: tag << 48 | creators << 24 | arrivals (inclusive prefix of a tile)
+    double red[NT / 32 + 1];
+    u32 ord[HC], cnt[HC], soff[HC];
     alignas(16) int cand[CC];
-    int arr[CC], aoff[CC + 1], slot_of[CC];
+    int sarr[CC];
+    int2 mlist[CC / 2 + 1];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
-    int ints[4];
+    int ints[8];                    // 0 queue ticket, 1 head count, 2 status, 3 arena exhausted, 4 new states, 5 arrivals, 6 multi-arrival states
 };
 
-template <int NT, int CC, int CL, int KMAX, int MINB>
+template <int NT, int CC, int MINB>
 __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 {
-    typedef FwdSmem<NT, CC, CL, KMAX> Smem;
+    typedef FwdSmem<NT, CC> Smem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    constexpr u32 FULL = 0xffffffffu;
+    constexpr u32 SLOT_MASK = 0x3FFFFFFFu;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
     const DevPanel &pn = p.panel;
     const DevModel &md = p.model;
-    const int L = pn.L, A = md.Amax, K = p.K, head_len = md.head_len;
+    const int L = pn.L, A = md.Amax, head_len = md.head_len;
+    const bool estep = p.estep != 0;
     const Scratch sc = p.scratch[blockIdx.x];
-    double *const sc_like0 = sc.like[0], *const sc_like1 = sc.like[1];
-    u64 *const sc_meta0 = sc.meta[0], *const sc_meta1 = sc.meta[1];
     u64 *const arena = p.arena.base;
     const int4 *const succ16 = reinterpret_cast<const int4 *>(md.succ16);
 
     if (tid == 0) { sm.ll[2] = 0; sm.ll[3] = 0; }
+    for (int h = tid; h < Smem::HC; h += NT) { sm.keys[h] = KEY_EMPTY; sm.ord[h] = 0xFFFFFFFFu; sm.cnt[h] = 0; }
 
     // chunked bump allocation (thread 0 only); returns -1 when the arena is exhausted
     auto alloc = [&](long long units) -> long long {
@@ -116,7 +96,11 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         if (sm.ll[2] + units > sm.ll[3]) {
             const long long grab = units > CHUNK ? units : CHUNK;
             const unsigned long long base = atomicAdd(p.arena.cursor, (unsigned long long) grab);
-            if ((long long) (base + grab) > p.arena.capacity) { atomicExch(p.arena.exhausted, 1); return -1; }
+            if ((long long) (base + grab) > p.arena.capacity) {
+                atomicAdd(p.arena.cursor, (unsigned long long) (-grab));       // give it back: the K-best kernel allocates behind the trellis
+                atomicExch(p.arena.exhausted, 1);
+                return -1;
+            }
             sm.ll[2] = (long long) base; sm.ll[3] = (long long) base + grab;
         }
         const long long off = sm.ll[2];
@@ -126,12 +110,14 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
     for (;;) {
         block_sync<NT>();
-        if (tid == 0) sm.ints[0] = atomicAdd(p.queue, 1);
+        if (tid == 0) { sm.ints[0] = atomicAdd(p.queue, 1); sm.ints[3] = *(volatile int *) p.arena.exhausted; }     // one read per CTA: the decision is block-uniform
         block_sync<NT>();
         const int w = sm.ints[0];
         if (w >= p.n_wave) break;
-        if (*(volatile int *) p.arena.exhausted) { if (tid == 0) p.status[w] = ST_NOMEM; continue; }
+        if (sm.ints[3]) { if (tid == 0) p.status[w] = ST_NOMEM; continue; }
         const long long t_begin = clock64();
+        long long t_begin_ns = 0;
+        if (p.ind_cycles) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); t_begin_ns = (long long) t_; }
         const int ind = p.wave[w];
         const u32 *gp = pn.packed + (size_t) ind * pn.words;
         LocusRec *rec = p.loci + (size_t) w * (L + 1);
@@ -178,7 +164,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                         if (hp < 0) { bad = 1; break; }
                         if (hp >= head) {
                             if (nh < CC) { sm.ida[0][nh] = head; sm.idb[0][nh] = hp; }
-                            if (nh < sc.scap && 2 * nh + 1 < sc.ccap) { sc.cand[2 * nh] = head; sc.cand[2 * nh + 1] = hp; }    // staging when nh >= CC
+                            if (2 * nh + 1 < sc.ccap) { sc.cand[2 * nh] = head; sc.cand[2 * nh + 1] = hp; }    // staging when nh >= CC
                             ++nh;
                         }
                     }
@@ -191,31 +177,29 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             int st = ST_DONE;
             if (bad) st = ST_NO_HEAD;
             else if (nh > sc.scap || 2 * nh > sc.ccap) st = ST_TOO_BIG;
-            else if (nh > 0) { off = alloc(block_layout(nh, K, p.estep).total); if (off < 0) st = ST_NOMEM; }
+            else if (nh > 0) { off = alloc(block_layout(nh, 0, p.estep).total); if (off < 0) st = ST_NOMEM; }
             sm.ints[1] = nh; sm.ints[2] = st; sm.ll[1] = off;
         }
         block_sync<NT>();
         S_in = sm.ints[1]; status = sm.ints[2]; cur_off = sm.ll[1];
         if (status != ST_DONE) { if (tid == 0) p.status[w] = status; continue; }
         {
-            const BlockLayout bl = block_layout(S_in, K, p.estep);
+            const BlockLayout bl = block_layout(S_in, 0, p.estep);
             int *t_ida = (int *) (arena + cur_off + bl.ida), *t_idb = (int *) (arena + cur_off + bl.idb);
             double *t_alpha = (double *) (arena + cur_off + bl.alpha);
             unsigned char *t_ab = (unsigned char *) (arena + cur_off + bl.ab);
-            u32 *t_bp = (u32 *) (arena + cur_off + bl.bp);
+            double *t_v1 = (double *) (arena + cur_off + bl.v1);
+            int *t_aoff = (int *) (arena + cur_off + bl.aoff);
             double *t_tp = (double *) (arena + cur_off + bl.tp);
             for (int s = tid; s < S_in; s += NT) {
                 const int a = s < CC ? sm.ida[0][s] : sc.cand[2 * s], b = s < CC ? sm.idb[0][s] : sc.cand[2 * s + 1];
                 const double f = __dmul_rn(md.freq[a], md.freq[b]);
                 const double al = (a == b) ? f : __dmul_rn(f, 2.0);
-                if (s < CC) sm.alpha[0][s] = al;
+                if (s < CC) { sm.alpha[0][s] = al; sm.v1[0][s] = f; }
                 t_ida[s] = a; t_idb[s] = b; t_alpha[s] = al;
                 t_ab[s] = (unsigned char) (md.last[a] | (md.last[b] << 4));
-                if (p.estep) t_tp[s] = f;
-                else t_bp[(size_t) s * K] = BP_HEAD | (a == b ? BP_HOM : 0u);
-                const u64 mt = 1ull | ((a == b ? 1ull : 0ull) << 8);
-                if (S_in <= CL) { sm.like[0][s * KMAX] = f; sm.meta[0][s] = mt; }
-                else { sc_like0[(size_t) s * K] = f; sc_meta0[s] = mt; }
+                if (estep) t_tp[s] = f;
+                else { t_v1[s] = f; t_aoff[s] = 0; if (s == 0) t_aoff[S_in] = 0; }
             }
             if (tid == 0) { rec[head_len].off = cur_off; rec[head_len].count = S_in; }
         }
@@ -250,7 +234,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             else if (g0 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g1); }
             else if (g1 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g0); }
             else add_group(g0, g1);
-            if (tid == 0) sm.gbase[ng] = C;
+            if (tid == 0) { sm.gbase[ng] = C; sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; }
+            if (tid < 8) sm.look[tid] = 0;
             int hsize = 64;
             while (hsize * 4 < 5 * C) hsize <<= 1;     // load factor <= 0.8 even if every candidate were a new state
             const bool fast = (C <= CC);
@@ -265,40 +250,40 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             long long new_off = 0;
 
             // The step body; FAST selects shared-memory work arrays (compile-time, so the accesses are LDS/STS/ATOMS).
+            // returns 0 = ok, 1 = every extension died, 2 = status set (the hash arrays were reset)
             auto body = [&](auto fast_tag) -> int {
                 constexpr bool FAST = decltype(fast_tag)::value;
                 u64 *const keys = FAST ? sm.keys : sc.keys;
                 double *const tpvs = FAST ? sm.tpv : sc.tpv;
                 u32 *const ord = FAST ? sm.ord : sc.ord;
                 u32 *const cnt = FAST ? sm.cnt : sc.cnt;
+                u32 *const soff = FAST ? sm.soff : sc.soff;
                 int *const cand = FAST ? sm.cand : sc.cand;
-                int *const arr = FAST ? sm.arr : sc.arr;
-                int *const aoff = FAST ? sm.aoff : sc.aoff;
-                int *const slot_of = FAST ? sm.slot_of : sc.slot_of;
+                int *const sarr = FAST ? sm.sarr : sc.sarr;
+                int2 *const mlist = FAST ? sm.mlist : sc.mlist;
                 const u32 hmask = (u32) hsize - 1u;
-                for (int h = tid; h < hsize; h += NT) { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
+                auto reset_table = [&]() {      // error exits: leave the hash arrays all-empty for the next individual
+                    block_sync<NT>();
+                    for (int h = tid; h < hsize; h += NT) { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
+                };
 
                 // input state views
-                const BlockLayout bli = block_layout(S_in, K, p.estep);
+                const BlockLayout bli = block_layout(S_in, 0, p.estep);
                 const int *gi_ida = (const int *) (arena + cur_off + bli.ida), *gi_idb = (const int *) (arena + cur_off + bli.idb);
                 const double *gi_alpha = (const double *) (arena + cur_off + bli.alpha);
+                const double *gi_v1 = (const double *) (arena + cur_off + bli.v1);
                 const bool in_cache = FAST || S_in <= CC;       // FAST implies S_in <= C <= CC
                 const int *ci_ida = sm.ida[par], *ci_idb = sm.idb[par];
-                const double *ci_alpha = sm.alpha[par];
-                const bool lk_in_cache = S_in <= CL;
-                const double *like_in = par ? sc_like1 : sc_like0;
-                const u64 *meta_in = par ? sc_meta1 : sc_meta0;
-                double *like_out = par ? sc_like0 : sc_like1;
-                u64 *meta_out = par ? sc_meta0 : sc_meta1;
+                const double *ci_alpha = sm.alpha[par], *ci_v1 = sm.v1[par];
 
                 // forward-link block of index i (E-step mode)
                 long long fwd_off = 0;
-                if (p.estep && tid == 0) sm.ll[1] = alloc(((long long) C + 1) / 2);
-                block_sync<NT>();       // hash cleared, groups visible, fwd allocation visible
+                if (estep && tid == 0) sm.ll[1] = alloc(((long long) C + 1) / 2);
+                block_sync<NT>();       // groups / counters / look-back ring visible, fwd allocation visible
                 PASS_MARK(0);
-                if (p.estep) {
+                if (estep) {
                     fwd_off = sm.ll[1];
-                    if (fwd_off < 0) { status = ST_NOMEM; return 2; }
+                    if (fwd_off < 0) { status = ST_NOMEM; return 2; }       // nothing inserted yet: the hash arrays are clean
                     if (tid == 0) { rec[i].fwd_off = fwd_off; rec[i].fwd_slots = C; }
                 }
                 int *fwd = (int *) (arena + fwd_off);
@@ -310,275 +295,299 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     if (sm.gx[g] != sm.gy[g]) { s = r >> 1; dir = r & 1; } else { s = r; dir = 0; }
                 };
 
-                // ---- pass A: gather successors (two candidates in flight per lane), canonicalise, hash-insert ----
-                for (int c0 = tid; c0 < C; c0 += 2 * NT) {
-                    const int cc[2] = {c0, c0 + NT};
-                    bool live[2];
-                    int4 ea[2], eb[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        live[q] = false;
-                        if (cc[q] < C) {
-                            int g, s, dir;
-                            decode(cc[q], g, s, dir);
-                            const int x = dir ? sm.gy[g] : sm.gx[g], y = dir ? sm.gx[g] : sm.gy[g];
-                            const int pa = in_cache ? ci_ida[s] : gi_ida[s], pb = in_cache ? ci_idb[s] : gi_idb[s];
-                            const double al = in_cache ? ci_alpha[s] : gi_alpha[s];
-                            if (al > 0.0) {     // HaploBuilder.cpp:237
-                                live[q] = true;
-                                ea[q] = __ldcg(succ16 + (size_t) pa * A + x);     // L2 only: the 150 MB table would only evict the lists and hash from L1
-                                eb[q] = __ldcg(succ16 + (size_t) pb * A + y);
-                            }
-                        }
+                // ---- pass A: lanes over predecessor states; gather successors, canonicalise, hash-insert ----
+                int my_new = 0, my_arr = 0;
+                for (int s = tid; s < S_in; s += NT) {
+                    const int pa = in_cache ? ci_ida[s] : gi_ida[s], pb = in_cache ? ci_idb[s] : gi_idb[s];
+                    const double al = in_cache ? ci_alpha[s] : gi_alpha[s];
+                    const bool alive = al > 0.0;       // HaploBuilder.cpp:237
+                    const int4 *ra = succ16 + (size_t) pa * A, *rb = succ16 + (size_t) pb * A;
+                    int4 ea0 = make_int4(-1, 0, 0, 0), ea1 = ea0, eb0 = ea0, eb1 = ea0;
+                    if (alive && A == 2) {      // biallelic: both entries of a row share one 32-byte sector
+                        ea0 = __ldcg(ra); ea1 = __ldcg(ra + 1); eb0 = __ldcg(rb); eb1 = __ldcg(rb + 1);
                     }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (cc[q] >= C) continue;
-                        int enc = -1;
-                        if (live[q]) {
-                            int hpa = ea[q].x, hpb = eb[q].x;
-                            if (hpa >= 0 && hpb >= 0) {
-                                const double tv = __dmul_rn(__hiloint2double(ea[q].w, ea[q].z), __hiloint2double(eb[q].w, eb[q].z));
-                                u32 rev = 0;
-                                if (hpa > hpb) { const int t = hpa; hpa = hpb; hpb = t; rev = 1; }
-                                const u64 key = ((u64) (u32) hpa << 32) | (u32) hpb;
-                                u32 h = mix64(key) & hmask;
-                                for (;;) {
-                                    const u64 prev = atomicCAS(keys + h, KEY_EMPTY, key);
-                                    if (prev == KEY_EMPTY) { tpvs[h] = tv; break; }
-                                    if (prev == key) break;
-                                    h = (h + 1) & hmask;
-                                }
-                                atomicMin(ord + h, (u32) cc[q]);
-                                atomicAdd(cnt + h, 1u);
-                                enc = (int) (h | (rev << 30));
+                    for (int g = 0; g < ng; ++g) {
+                        const int x = sm.gx[g], y = sm.gy[g];
+                        const bool het = x != y;
+                        const int c0 = sm.gbase[g] + (het ? 2 * s : s);
+                        const int nd = het ? 2 : 1;
+                        int4 ea[2], eb[2];
+                        ea[0] = ea[1] = eb[0] = eb[1] = make_int4(-1, 0, 0, 0);
+                        if (alive) {
+                            if (A == 2) {
+                                ea[0] = x ? ea1 : ea0; eb[0] = y ? eb1 : eb0;
+                                ea[1] = y ? ea1 : ea0; eb[1] = x ? eb1 : eb0;
+                            }
+                            else {
+                                ea[0] = __ldcg(ra + x); eb[0] = __ldcg(rb + y);
+                                if (het) { ea[1] = __ldcg(ra + y); eb[1] = __ldcg(rb + x); }
                             }
                         }
-                        cand[cc[q]] = enc;
-                        if (p.estep && enc < 0) fwd[cc[q]] = -1;
+                        // both orientations: keys first, then the two compare-and-swaps in flight together
+                        u64 key[2];
+                        u32 hh[2], rev[2];
+                        double tv[2];
+                        bool ok[2];
+                        u64 prev[2];
+#pragma unroll
+                        for (int d = 0; d < 2; ++d) {
+                            ok[d] = alive && d < nd && ea[d].x >= 0 && eb[d].x >= 0;
+                            key[d] = 0; hh[d] = 0; rev[d] = 0; tv[d] = 0.0; prev[d] = 0;
+                            if (ok[d]) {
+                                int hpa = ea[d].x, hpb = eb[d].x;
+                                tv[d] = __dmul_rn(__hiloint2double(ea[d].w, ea[d].z), __hiloint2double(eb[d].w, eb[d].z));
+                                if (hpa > hpb) { const int t = hpa; hpa = hpb; hpb = t; rev[d] = 1; }
+                                key[d] = ((u64) (u32) hpa << 32) | (u32) hpb;
+                                hh[d] = mix64(key[d]) & hmask;
+                                prev[d] = atomicCAS(keys + hh[d], KEY_EMPTY, key[d]);
+                            }
+                        }
+#pragma unroll
+                        for (int d = 0; d < 2; ++d) {
+                            if (d >= nd) continue;
+                            int enc = -1;
+                            if (ok[d]) {
+                                u32 h = hh[d];
+                                u64 pv = prev[d];
+                                for (;;) {
+                                    if (pv == KEY_EMPTY) { tpvs[h] = tv[d]; ++my_new; break; }
+                                    if (pv == key[d]) break;
+                                    h = (h + 1) & hmask;
+                                    pv = atomicCAS(keys + h, KEY_EMPTY, key[d]);
+                                }
+                                atomicMin(ord + h, (u32) (c0 + d));
+                                atomicAdd(cnt + h, 1u);
+                                ++my_arr;
+                                enc = (int) (h | (rev[d] << 30));
+                            }
+                            cand[c0 + d] = enc;
+                            if (estep && enc < 0) fwd[c0 + d] = -1;
+                        }
                     }
                 }
+                // new states / arrivals of the step
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { my_new += __shfl_xor_sync(FULL, my_new, o); my_arr += __shfl_xor_sync(FULL, my_arr, o); }
+                if (lane == 0 && my_arr) { atomicAdd(&sm.ints[4], my_new); atomicAdd(&sm.ints[5], my_arr); }
                 block_sync<NT>();
                 PASS_MARK(1);
+                S_out = sm.ints[4];
+                const int n_arr = sm.ints[5];
+                if (S_out == 0) return 1;       // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82 (nothing was inserted)
+                if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; reset_table(); return 2; }
+                if (tid == 0) sm.ll[1] = alloc(block_layout(S_out, n_arr, p.estep).total);
+                block_sync<NT>();
+                new_off = sm.ll[1];
+                if (new_off < 0) { status = ST_NOMEM; reset_table(); return 2; }
+                c_arr += n_arr;
 
-                // ---- pass B+C: creators in ordinal order -> new state indices and arrival-segment offsets ----
-                // each lane owns UB consecutive ordinals, so the loads of a lane are independent and one block scan serves UB*NT slots
-                int n_arr = 0;
-                constexpr int UB = 4;
-                for (int base = 0; base < C; base += NT * UB) {
-                    const int c0 = base + tid * UB;
-                    int enc[UB], nn[UB];
-                    bool cr[UB];
-                    u32 ov[UB];
-                    if (c0 + UB <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
-                    else {
+                const BlockLayout blo = block_layout(S_out, n_arr, p.estep);
+                int *t_ida = (int *) (arena + new_off + blo.ida), *t_idb = (int *) (arena + new_off + blo.idb);
+                double *t_alpha = (double *) (arena + new_off + blo.alpha);
+                double *t_v1 = (double *) (arena + new_off + blo.v1);
+                unsigned char *t_ab = (unsigned char *) (arena + new_off + blo.ab);
+                int *t_aoff = (int *) (arena + new_off + blo.aoff);
+                u32 *t_arr = (u32 *) (arena + new_off + blo.arr);
+                double *t_tp = (double *) (arena + new_off + blo.tp);
+                int *co_ida = sm.ida[par ^ 1], *co_idb = sm.idb[par ^ 1];
+                double *co_alpha = sm.alpha[par ^ 1], *co_v1 = sm.v1[par ^ 1];
+                const bool out_cache = S_out <= CC;
+                double amax = 0.0;
+                if (!estep && tid == 0) t_aoff[S_out] = n_arr;
+
+                // ---- pass C: creators in ordinal order -> state indices and arrival offsets; single-arrival states are finished here ----
+                {
+                    const int ntiles = (C + 127) >> 7;
+                    for (int tile = wid; tile < ntiles; tile += NW) {
+                        const int c0 = (tile << 7) + lane * 4;
+                        int enc[4], nn[4];
+                        bool cr[4];
+                        u32 ov[4];
+                        if (c0 + 4 <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
+                        else {
 #pragma unroll
-                        for (int u = 0; u < UB; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
-                    }
+                            for (int u = 0; u < 4; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
+                        }
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & 0x3FFFFFFF] : 0xFFFFFFFFu;
-                    int ncr = 0, nar = 0;
+                        for (int u = 0; u < 4; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & SLOT_MASK] : 0xFFFFFFFFu;
+                        int ncr = 0, nar = 0;
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
-                        nn[u] = cr[u] ? (int) cnt[enc[u] & 0x3FFFFFFF] : 0;
-                        ncr += cr[u] ? 1 : 0;
-                    }
+                        for (int u = 0; u < 4; ++u) {
+                            cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
+                            nn[u] = cr[u] ? (int) cnt[enc[u] & SLOT_MASK] : 0;
+                            ncr += cr[u] ? 1 : 0;
+                            nar += nn[u];
+                        }
+                        int xs = ncr, xa = nar;
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) nar += nn[u];
-                    // one scan for both: creators | arrivals
-                    long long tot;
-                    const long long ex = BlockScan<NT>::run(((long long) ncr << 40) | (long long) nar, tot, sm.tmp);
-                    int idx = S_out + (int) ((ex >> 40) & 0xFFF), off = n_arr + (int) (ex & 0xFFFFFFFFFFll);
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int ys = __shfl_up_sync(FULL, xs, o), ya = __shfl_up_sync(FULL, xa, o);
+                            if (lane >= o) { xs += ys; xa += ya; }
+                        }
+                        const int tot_cr = __shfl_sync(FULL, xs, 31), tot_ar = __shfl_sync(FULL, xa, 31);
+                        unsigned long long prevp = 0;
+                        if (lane == 0) {
+                            if (tile > 0) {
+                                volatile unsigned long long *slot = &sm.look[(tile - 1) & 7];
+                                const unsigned long long want = (unsigned long long) (tile & 0xFFFF);
+                                do { prevp = *slot; } while ((prevp >> 48) != want);
+                            }
+                            const unsigned long long b_idx = (prevp >> 24) & 0xFFFFFFull, b_off = prevp & 0xFFFFFFull;
+                            *(volatile unsigned long long *) &sm.look[tile & 7] =
+                                ((unsigned long long) ((tile + 1) & 0xFFFF) << 48) | ((b_idx + (unsigned long long) tot_cr) << 24) | (b_off + (unsigned long long) tot_ar);
+                        }
+                        prevp = __shfl_sync(FULL, prevp, 0);
+                        int idx = (int) ((prevp >> 24) & 0xFFFFFFull) + xs - ncr;
+                        int off = (int) (prevp & 0xFFFFFFull) + xa - nar;
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        if (cr[u]) {
-                            const int h = enc[u] & 0x3FFFFFFF;
-                            if (idx < sc.scap) {
-                                ord[h] = 0x80000000u | (u32) idx;     // never equals a later ordinal
-                                slot_of[idx] = h;
-                                aoff[idx] = off;
+                        for (int u = 0; u < 4; ++u) {
+                            if (!cr[u]) continue;
+                            const int c = c0 + u;
+                            const u32 h = (u32) enc[u] & SLOT_MASK;
+                            const u32 rev = ((u32) enc[u] >> 30) & 1u;
+                            const u64 key = keys[h];
+                            const double tv = tpvs[h];
+                            int g, s, dir;
+                            decode(c, g, s, dir);
+                            const int gxv = sm.gx[g], gyv = sm.gy[g];
+                            const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
+                            const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
+                            t_ida[idx] = hpa; t_idb[idx] = hpb;
+                            t_ab[idx] = (unsigned char) ((rev ? yy : xx) | ((rev ? xx : yy) << 4));
+                            if (estep) t_tp[idx] = tv; else t_aoff[idx] = off;
+                            if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; }
+                            if (nn[u] == 1) {
+                                const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
+                                const double alpha = __dmul_rn(ain, tv);
+                                t_alpha[idx] = alpha;
+                                if (out_cache) co_alpha[idx] = alpha;
+                                amax = fmax(amax, alpha);
+                                if (!estep) {
+                                    const double v = __dmul_rn(in_cache ? ci_v1[s] : gi_v1[s], tv);
+                                    t_v1[idx] = v;
+                                    if (out_cache) co_v1[idx] = v;
+                                    t_arr[off] = (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u);
+                                }
+                                else fwd[c] = (int) ((u32) idx | (rev << 31));
+                                keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0;
+                                cand[c] = -1;
+                            }
+                            else {
+                                ord[h] = 0x80000000u | (u32) idx;     // never equals an ordinal
                                 cnt[h] = 0;
+                                soff[h] = (u32) off;
+                                const int m = atomicAdd(&sm.ints[6], 1);
+                                mlist[m] = make_int2(idx, (int) h);
                             }
                             ++idx; off += nn[u];
                         }
                     }
-                    S_out += (int) ((tot >> 40) & 0xFFF);
-                    n_arr += (int) (tot & 0xFFFFFFFFFFll);
                 }
-                if (S_out == 0) return 1;       // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82
-                if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; return 2; }
-                if (tid == 0) { sm.ll[1] = alloc(block_layout(S_out, K, p.estep).total); aoff[S_out] = n_arr; }
-                c_arr += n_arr;
                 block_sync<NT>();
-                new_off = sm.ll[1];
-                if (new_off < 0) { status = ST_NOMEM; return 2; }
                 PASS_MARK(2);
+                const int n_multi = sm.ints[6];
 
-                // ---- pass D: scatter arrivals (unordered inside a segment; sorted in E) ----
-                for (int base = 0; base < C; base += NT * UB) {
-                    const int c0 = base + tid * UB;
-                    int enc[UB], idxv[UB], pos[UB];
-                    if (c0 + UB <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
-                    else {
+                // ---- pass D: scatter the arrivals of multi-arrival states (unordered inside a segment; sorted in E) ----
+                if (n_multi > 0) {
+                    for (int base = 0; base < C; base += NT * 4) {
+                        const int c0 = base + tid * 4;
+                        int enc[4];
+                        if (c0 + 4 <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
+                        else {
 #pragma unroll
-                        for (int u = 0; u < UB; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
-                    }
+                            for (int u = 0; u < 4; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
+                        }
+                        u32 so[4], pos[4], ov[4];
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        idxv[u] = 0; pos[u] = 0;
-                        if (enc[u] >= 0) { const int h = enc[u] & 0x3FFFFFFF; idxv[u] = (int) (ord[h] & 0x7FFFFFFFu); pos[u] = (int) atomicAdd(cnt + h, 1u); }
-                    }
+                        for (int u = 0; u < 4; ++u) {
+                            so[u] = 0; pos[u] = 0; ov[u] = 0;
+                            if (enc[u] >= 0) {
+                                const u32 h = (u32) enc[u] & SLOT_MASK;
+                                so[u] = soff[h];
+                                pos[u] = atomicAdd(cnt + h, 1u);
+                                if (estep) ov[u] = ord[h];
+                            }
+                        }
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        if (enc[u] >= 0) {
-                            const u32 rev = ((u32) enc[u] >> 30) & 1u;
-                            arr[aoff[idxv[u]] + pos[u]] = (int) ((u32) (c0 + u) | (rev << 31));
-                            if (p.estep) fwd[c0 + u] = (int) ((u32) idxv[u] | (rev << 31));
+                        for (int u = 0; u < 4; ++u) {
+                            if (enc[u] >= 0) {
+                                const u32 rev = ((u32) enc[u] >> 30) & 1u;
+                                sarr[so[u] + pos[u]] = (int) ((u32) (c0 + u) | (rev << 31));
+                                if (estep) fwd[c0 + u] = (int) ((ov[u] & 0x7FFFFFFFu) | (rev << 31));
+                            }
                         }
                     }
+                    block_sync<NT>();
                 }
-                block_sync<NT>();
                 PASS_MARK(3);
 
-                // ---- pass E: one lane per new state ----
-                const BlockLayout blo = block_layout(S_out, K, p.estep);
-                int *t_ida = (int *) (arena + new_off + blo.ida), *t_idb = (int *) (arena + new_off + blo.idb);
-                double *t_alpha = (double *) (arena + new_off + blo.alpha);
-                unsigned char *t_ab = (unsigned char *) (arena + new_off + blo.ab);
-                u32 *t_bp = (u32 *) (arena + new_off + blo.bp);
-                double *t_tp = (double *) (arena + new_off + blo.tp);
-                int *co_ida = sm.ida[par ^ 1], *co_idb = sm.idb[par ^ 1];
-                double *co_alpha = sm.alpha[par ^ 1];
-                const bool out_cache = S_out <= CC;
-                const bool lk_out_cache = S_out <= CL;
-                double amax = 0.0;
-                for (int idx = tid; idx < S_out; idx += NT) {
-                    const int h = slot_of[idx];
-                    const u64 key = keys[h];
-                    const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
-                    const double tpv = tpvs[h];
-                    const int a0 = aoff[idx], n = aoff[idx + 1] - a0;
-                    // ordinal order inside the segment: up to 8 arrivals are sorted in registers (one batch of loads, a
-                    // 19-comparator network, one batch of stores); longer segments (< 1 % of arrivals) by insertion in place
-                    if (n > 1 && n <= 8) {
+                // ---- pass E: one lane per multi-arrival state ----
+                for (int m = tid; m < n_multi; m += NT) {
+                    const int2 me = mlist[m];
+                    const int idx = me.x;
+                    const u32 h = (u32) me.y;
+                    const double tv = tpvs[h];
+                    const int a0 = (int) soff[h], n = (int) cnt[h];
+                    keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0;
+                    double alpha = 0.0, vmax = 0.0;
+                    auto take = [&](int e, int j) {
+                        int g, s, dir;
+                        decode(e & 0x7FFFFFFF, g, s, dir);
+                        const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
+                        const double term = __dmul_rn(ain, tv);
+                        alpha = (j == 0) ? term : __dadd_rn(alpha, term);
+                        if (!estep) {
+                            vmax = fmax(vmax, in_cache ? ci_v1[s] : gi_v1[s]);
+                            t_arr[a0 + j] = (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u);
+                        }
+                    };
+                    if (n <= 8) {
+                        // ordinal order inside the segment: up to 8 arrivals are sorted in registers (19-comparator network)
                         int v[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = (q < n) ? arr[a0 + q] : 0x7FFFFFFF;
+                        for (int q = 0; q < 8; ++q) v[q] = (q < n) ? sarr[a0 + q] : 0x7FFFFFFF;
                         auto cx = [&](int a, int b) { const int x = v[a], y = v[b]; const bool sw = (x & 0x7FFFFFFF) > (y & 0x7FFFFFFF); v[a] = sw ? y : x; v[b] = sw ? x : y; };
-                        cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
-                        cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
-                        cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
-                        cx(1, 5); cx(2, 6);
-                        cx(1, 4); cx(3, 6);
-                        cx(2, 4); cx(3, 5);
-                        cx(3, 4);
+                        if (n > 2) {
+                            cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
+                            cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
+                            cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
+                            cx(1, 5); cx(2, 6);
+                            cx(1, 4); cx(3, 6);
+                            cx(2, 4); cx(3, 5);
+                            cx(3, 4);
+                        }
+                        else cx(0, 1);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) if (q < n) arr[a0 + q] = v[q];
+                        for (int q = 0; q < 8; ++q) if (q < n) take(v[q], q);
                     }
                     else {
                         for (int j = 1; j < n; ++j) {
-                            const int e = arr[a0 + j];
+                            const int e = sarr[a0 + j];
                             int q = j - 1;
-                            while (q >= 0 && (arr[a0 + q] & 0x7FFFFFFF) > (e & 0x7FFFFFFF)) { arr[a0 + q + 1] = arr[a0 + q]; --q; }
-                            arr[a0 + q + 1] = e;
+                            while (q >= 0 && (sarr[a0 + q] & 0x7FFFFFFF) > (e & 0x7FFFFFFF)) { sarr[a0 + q + 1] = sarr[a0 + q]; --q; }
+                            sarr[a0 + q + 1] = e;
                         }
+                        for (int j = 0; j < n; ++j) take(sarr[a0 + j], j);
                     }
-                    double alpha = 0.0;
-                    double bl[KMAX];
-                    u32 bb[KMAX];
-                    int nl_out = 0, xa = 0, ya = 0;
-                    // software pipeline over the arrivals: the predecessor's alpha and list header of arrival j+1 are requested
-                    // before arrival j is merged (the list itself is read in one batch of independent loads)
-                    int nx_e = arr[a0], nx_g, nx_s, nx_dir;
-                    decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
-                    u64 nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
-                    double nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
-                    double nx_l0 = lk_in_cache ? sm.like[par][nx_s * KMAX] : like_in[(size_t) nx_s * K];    // every list has >= 1 link
-                    for (int j = 0; j < n; ++j) {
-                        const int e = nx_e, g = nx_g, s = nx_s, dir = nx_dir;
-                        const u64 mt = nx_mt;
-                        const double ain = nx_ain;
-                        const double l0 = nx_l0;
-                        const int nl = (int) (mt & 0xFF);
-                        // the predecessor's list (sorted descending) is read straight from where it lives: the first arrival copies it in one
-                        // batch of independent loads, later arrivals stream it with the next element always in flight
-                        const double *lp = lk_in_cache ? &sm.like[par][s * KMAX] : like_in + (size_t) s * K;
-                        if (j + 1 < n) {
-                            nx_e = arr[a0 + j + 1];
-                            decode(nx_e & 0x7FFFFFFF, nx_g, nx_s, nx_dir);
-                            nx_mt = lk_in_cache ? sm.meta[par][nx_s] : meta_in[nx_s];
-                            nx_ain = in_cache ? ci_alpha[nx_s] : gi_alpha[nx_s];
-                            nx_l0 = lk_in_cache ? sm.like[par][nx_s * KMAX] : like_in[(size_t) nx_s * K];
-                        }
-                        const u32 rev = (u32) e >> 31;
-                        const bool het = (sm.gx[g] != sm.gy[g]);
-                        if (j == 0) { const int xx = dir ? sm.gy[g] : sm.gx[g], yy = dir ? sm.gx[g] : sm.gy[g]; xa = rev ? yy : xx; ya = rev ? xx : yy; }
-                        u32 hom = (u32) (mt >> 8);
-                        const double term = __dmul_rn(ain, tpv);
-                        alpha = (j == 0) ? term : __dadd_rn(alpha, term);
-                        nl_out += nl;
-                        // het-locus rule (HaploPair.cpp:53-60,77-84): links still flagged homozygous lose the flag, and
-                        // are zeroed when this arrival is reversed
-                        const u32 zero = (het && rev) ? hom : 0u;
-                        if (het) hom = 0;
-                        const u32 bpbase = (u32) s | (rev ? BP_REV : 0u);
-                        if (j == 0 && zero == 0) {
-                            // scaling keeps the order: the first arrival's list is the initial top-K as it stands
-#pragma unroll
-                            for (int k = 0; k < KMAX; ++k) {
-                                bl[k] = (k < nl) ? __dmul_rn(lp[k], tpv) : -1.0;
-                                bb[k] = bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u);
-                            }
-                        }
-                        else {
-                            if (j == 0) {
-#pragma unroll
-                                for (int k = 0; k < KMAX; ++k) { bl[k] = -1.0; bb[k] = 0; }
-                            }
-                            // sorted input: stop at the first element that does not make the list (unless some were zeroed)
-                            int k = 0;
-                            double cur = l0;
-                            while (k < nl) {
-                                const double nxt = (k + 1 < nl) ? lp[k + 1] : 0.0;
-                                double lv = __dmul_rn(cur, tpv);
-                                if ((zero >> k) & 1u) lv = 0.0;
-                                if (lv > bl[KMAX - 1]) topk_insert<KMAX>(bl, bb, lv, bpbase | ((u32) k << BP_PRED_BITS) | (((hom >> k) & 1u) ? BP_HOM : 0u));
-                                else if (zero == 0) break;
-                                cur = nxt;
-                                ++k;
-                            }
-                        }
-                    }
-                    if (nl_out > K) nl_out = K;
-                    u32 hom_out = 0;
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        if (k < nl_out) {
-                            if (lk_out_cache) sm.like[par ^ 1][idx * KMAX + k] = bl[k];
-                            else like_out[(size_t) idx * K + k] = bl[k];
-                            if (!p.estep) t_bp[(size_t) idx * K + k] = bb[k];
-                            if (bb[k] & BP_HOM) hom_out |= 1u << k;
-                        }
-                    }
-                    const u64 mo = (u64) nl_out | ((u64) hom_out << 8);
-                    if (lk_out_cache) sm.meta[par ^ 1][idx] = mo; else meta_out[idx] = mo;
-                    t_ida[idx] = hpa; t_idb[idx] = hpb; t_alpha[idx] = alpha;
-                    t_ab[idx] = (unsigned char) (xa | (ya << 4));
-                    if (p.estep) t_tp[idx] = tpv;
-                    if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; co_alpha[idx] = alpha; }
+                    t_alpha[idx] = alpha;
+                    if (out_cache) co_alpha[idx] = alpha;
                     amax = fmax(amax, alpha);
+                    if (!estep) {
+                        const double v = __dmul_rn(vmax, tv);       // = max over arrivals of v1(pred) * tp: rounding is monotone
+                        t_v1[idx] = v;
+                        if (out_cache) co_v1[idx] = v;
+                    }
                 }
                 PASS_MARK(4);
                 if (p.scaled) {     // exponent-only rescale: mantissas stay those of the unscaled product
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(FULL, amax, o));
                     if (NT > 32) {
                         __syncthreads();
-                        if ((tid & 31) == 0) ((double *) sm.tmp)[tid >> 5] = amax;
+                        if (lane == 0) sm.red[wid] = amax;
                         __syncthreads();
                         amax = 0.0;
-                        for (int q = 0; q < NT / 32; ++q) amax = fmax(amax, ((double *) sm.tmp)[q]);
+                        for (int q = 0; q < NW; ++q) amax = fmax(amax, sm.red[q]);
                     }
                     if (amax > 0.0 && amax < 0x1p-512) {
                         block_sync<NT>();
@@ -586,13 +595,10 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             const double a2 = t_alpha[idx] * 0x1p+512;
                             t_alpha[idx] = a2;
                             if (out_cache) co_alpha[idx] = a2;
-                            if (lk_out_cache) {
-                                const int nl = (int) (sm.meta[par ^ 1][idx] & 0xFF);
-                                for (int k = 0; k < nl; ++k) sm.like[par ^ 1][idx * KMAX + k] *= 0x1p+512;
-                            }
-                            else {
-                                const int nl = (int) (meta_out[idx] & 0xFF);
-                                for (int k = 0; k < nl; ++k) like_out[(size_t) idx * K + k] *= 0x1p+512;
+                            if (!estep) {
+                                const double v2 = t_v1[idx] * 0x1p+512;
+                                t_v1[idx] = v2;
+                                if (out_cache) co_v1[idx] = v2;
                             }
                         }
                         new_exp += 512;
@@ -614,29 +620,14 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             PASS_MARK(5);
         }
         block_sync<NT>();
-        if (status == ST_DONE && S_in > 0 && !p.estep) {
-            // final link lists for the traceback kernel (selection over all final states' links)
-            if (tid == 0) sm.ll[1] = alloc((long long) S_in * K + S_in);
-            block_sync<NT>();
-            const long long fo = sm.ll[1];
-            if (fo < 0) status = ST_NOMEM;
-            else {
-                double *fl = (double *) (arena + fo);
-                u64 *fm = arena + fo + (long long) S_in * K;
-                const bool cached = S_in <= CL;
-                for (int s = tid; s < S_in; s += NT) {
-                    const u64 mt = cached ? sm.meta[par][s] : (par ? sc_meta1 : sc_meta0)[s];
-                    fm[s] = mt;
-                    const int nl = (int) (mt & 0xFF);
-                    for (int k = 0; k < nl; ++k) fl[(size_t) s * K + k] = cached ? sm.like[par][s * KMAX + k] : (par ? sc_like1 : sc_like0)[(size_t) s * K + k];
-                }
-                if (tid == 0) { rec[0].off = fo; rec[0].count = S_in; }     // index 0 is unused by the trellis when head_len >= 1
-            }
-        }
         if (tid == 0) {
             p.status[w] = status;
             p.final_exp[w] = cur_exp;
-            if (p.ind_cycles) p.ind_cycles[w] = clock64() - t_begin;
+            if (p.ind_cycles) {     // diagnostics: cycles, states, max states, arrivals, spill steps, start / end time (ns), CTA
+                long long *d = p.ind_cycles + (size_t) w * 8;
+                d[0] = clock64() - t_begin; d[1] = c_states; d[2] = c_max; d[3] = c_arr; d[4] = c_spill; d[5] = t_begin_ns;
+                unsigned long long t_end_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns)); d[6] = (long long) t_end_ns; d[7] = blockIdx.x;
+            }
             if (status == ST_DONE) {
                 atomicAdd((unsigned long long *) p.counters + 0, (unsigned long long) c_steps);
                 atomicAdd((unsigned long long *) p.counters + 1, (unsigned long long) c_states);

