@@ -234,10 +234,10 @@ __global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NT, int CC, int MINB>
-static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
+template <int NT, int CC, int MINB, bool ESTEP>
+static cudaError_t launch_forward_e(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
 {
-    auto kern = forward_kernel<NT, CC, MINB>;
+    auto kern = forward_kernel<NT, CC, MINB, ESTEP>;
     const size_t smem = sizeof(FwdSmem<NT, CC>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
@@ -246,9 +246,31 @@ static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
+template <int NT, int CC, int MINB>
+static cudaError_t launch_forward_t(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
+{
+    return p.estep ? launch_forward_e<NT, CC, MINB, true>(p, grid, st, max_blocks_per_sm) : launch_forward_e<NT, CC, MINB, false>(p, grid, st, max_blocks_per_sm);
+}
+
 // threads per individual -> kernel configuration (candidate slots of the shared-memory fast path, resident CTAs per SM)
 static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStream_t st, int *occ)
 {
+#ifdef FWD_SWEEP
+    if (const char *env = getenv("HMC_B200_FWD_CFG")) {     // kernel-configuration experiments
+        switch (atoi(env)) {
+            case 0: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
+            case 1: return launch_forward_t<256, 256, 4>(p, grid, st, occ);
+            case 2: return launch_forward_t<256, 512, 2>(p, grid, st, occ);
+            case 3: return launch_forward_t<256, 1024, 2>(p, grid, st, occ);
+            case 4: return launch_forward_t<512, 512, 2>(p, grid, st, occ);
+            case 5: return launch_forward_t<512, 1024, 1>(p, grid, st, occ);
+            case 6: return launch_forward_t<512, 1024, 2>(p, grid, st, occ);
+            case 7: return launch_forward_t<1024, 2048, 1>(p, grid, st, occ);
+            case 8: return launch_forward_t<256, 512, 4>(p, grid, st, occ);
+            default: break;
+        }
+    }
+#endif
     switch (nt) {
         case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
         case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
@@ -272,16 +294,15 @@ static int build_pool(hmc_ctx *ctx, ScratchPool &pl, int slots, int scap, int cc
         Scratch &s = h[i];
         s.hcap = hcap; s.ccap = ccap; s.scap = scap;
         s.keys = (u64 *) b; b += b_keys;
-        s.tpv = (double *) b; b += b_keys;
         s.ord = (u32 *) b; b += b_u32;
         s.cnt = (u32 *) b; b += b_u32;
+        s.tpv = (double *) b; b += b_keys;
         s.soff = (u32 *) b; b += b_u32;
         s.cand = (int *) b; b += b_c;
         s.sarr = (int *) b; b += b_c;
         s.mlist = (int2 *) b; b += b_m;
-        CK(cudaMemsetAsync(s.keys, 0xFF, (size_t) hcap * 8, ctx->stream));
-        CK(cudaMemsetAsync(s.ord, 0xFF, (size_t) hcap * 4, ctx->stream));
-        CK(cudaMemsetAsync(s.cnt, 0, (size_t) hcap * 4, ctx->stream));
+        CK(cudaMemsetAsync(s.keys, 0xFF, b_keys + b_u32, ctx->stream));      // keys = KEY_EMPTY, ord = none
+        CK(cudaMemsetAsync(s.cnt, 0, b_u32, ctx->stream));
     }
     CK(cudaMemcpyAsync(pl.desc.p, h.data(), sizeof(Scratch) * slots, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -336,6 +357,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     const int nt = pick_threads(ctx);
     int occ = 1;
     FwdParams fp = {};
+    fp.estep = estep;
     CK(launch_forward(nt, fp, 0, ctx->stream, &occ));
     if (occ < 1) occ = 1;
     const int max_slots = ctx->sms * occ;

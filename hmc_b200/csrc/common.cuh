@@ -74,14 +74,14 @@ struct Arena {
 };
 
 // Per-CTA (persistent slot) spill scratch in global memory, used when a step does not fit the
-// shared-memory fast path.  The hash arrays are all-empty between steps (slots are reset by their owners).
+// shared-memory fast path.  The hash arrays are all-empty between steps (slots are released by their owners).
 struct Scratch {
     int hcap, ccap, scap;       // hash slots (power of two), candidate slots, states
     u64 *keys;                  // [hcap]
     double *tpv;                // [hcap] transition-probability product of the slot's state
     u32 *ord, *cnt, *soff;      // [hcap] smallest candidate ordinal -> state index; arrivals; arrival-segment offset
     int *cand, *sarr;           // [ccap] slot | rev << 30 of every candidate; arrival ordinals grouped by state
-    int2 *mlist;                // [scap] {state index, slot} of the states with more than one arrival
+    int2 *mlist;                // [scap] {state index, slot} of the states with more than one arrival (2..8 from the front, more from the back)
 };
 
 struct FwdParams {

@@ -43,31 +43,55 @@ namespace hmc {
 #define PASS_MARK(slot) do { } while (0)
 #endif
 
+// trellis outputs: written once, read much later (next step at the earliest, through L2) -> optionally streaming stores
+template <typename T>
+__device__ __forceinline__ void ST_OUT(T *p, T v)
+{
+#ifdef FWD_STREAM_OUT
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 template <int NT>
 __device__ __forceinline__ void block_sync()
 {
     if (NT == 32) __syncwarp(); else __syncthreads();
 }
 
+// The per-step state hash: separate arrays per field, in shared memory (fast path) or in the CTA's global spill scratch.
+// (One 32-byte record per slot was measured too: one sector per candidate instead of five, but the three or four atomics of a
+// candidate then queue on the same L2 sector, and in shared memory a 32-byte stride puts every field on 4 bank groups -- slower.)
+struct HashTab {
+    u64 *keys;          // (id_a << 32 | id_b), KEY_EMPTY = free
+    double *tpvs;       // transition-probability product of the state
+    u32 *ord;           // smallest candidate ordinal that reached the slot; 0x80000000 | state index once created
+    u32 *cnt;           // arrivals
+    u32 *soffs;         // offset of the state's arrival segment
+    __device__ __forceinline__ void release(u32 h) const { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
+    __device__ __forceinline__ void created(u32 h, u32 idx, u32 off) const { ord[h] = 0x80000000u | idx; cnt[h] = 0; soffs[h] = off; }
+};
+
 template <int NT, int CC>
 struct FwdSmem {
     static constexpr int HC = 2 * CC <= 256 ? 256 : 2 * CC <= 512 ? 512 : 2 * CC <= 1024 ? 1024 : 2 * CC <= 2048 ? 2048 : 4096;   // power of two >= 2 CC
     u64 keys[HC];
     double tpv[HC];
+    u32 ord[HC], cnt[HC], soff[HC];
     double alpha[2][CC], v1[2][CC];
     long long ll[4];                // -, alloc result, chunk cursor, chunk end
     unsigned long long look[8];     // look-back ring of pass C: tag << 48 | creators << 24 | arrivals (inclusive prefix of a tile)
     double red[NT / 32 + 1];
-    u32 ord[HC], cnt[HC], soff[HC];
     alignas(16) int cand[CC];
     int sarr[CC];
     int2 mlist[CC / 2 + 1];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
-    int ints[8];                    // 0 queue ticket, 1 head count, 2 status, 3 arena exhausted, 4 new states, 5 arrivals, 6 multi-arrival states
+    int ints[8];                    // 0 queue ticket, 1 head count, 2 status, 3 arena exhausted, 4 new states, 5 arrivals, 6 / 7 states with 2..4 / more arrivals
 };
 
-template <int NT, int CC, int MINB>
+template <int NT, int CC, int MINB, bool ESTEP>
 __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 {
     typedef FwdSmem<NT, CC> Smem;
@@ -81,7 +105,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
     const DevPanel &pn = p.panel;
     const DevModel &md = p.model;
     const int L = pn.L, A = md.Amax, head_len = md.head_len;
-    const bool estep = p.estep != 0;
+    constexpr bool estep = ESTEP;
     const Scratch sc = p.scratch[blockIdx.x];
     u64 *const arena = p.arena.base;
     const int4 *const succ16 = reinterpret_cast<const int4 *>(md.succ16);
@@ -121,6 +145,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         const int ind = p.wave[w];
         const u32 *gp = pn.packed + (size_t) ind * pn.words;
         LocusRec *rec = p.loci + (size_t) w * (L + 1);
+#pragma unroll 1
         for (int l = tid; l <= L; l += NT) { rec[l].count = 0; rec[l].fwd_slots = 0; rec[l].off = 0; rec[l].fwd_off = 0; }
         const int gbits = pn.bits;
         const u32 gmask = (1u << gbits) - 1u;
@@ -132,11 +157,14 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         if (tid == 0) {
             int nh = 0, bad = 0;
             int hg0[8], hg1[8];
+#pragma unroll 1
             for (int j = 0; j < head_len; ++j) { const u32 wd = geno_word(j); hg0[j] = (int) (wd & gmask) - 1; hg1[j] = (int) ((wd >> gbits) & gmask) - 1; }
+#pragma unroll 1
             for (int hi = 0; hi < md.n_heads && !bad; ++hi) {
                 const int head = md.heads[hi];
                 const signed char *ha = md.al + md.al_off[head];
                 bool match = true;
+#pragma unroll 1
                 for (int j = 0; j < head_len; ++j) {
                     const int a = ha[j];
                     if (!(hg0[j] < 0 || hg1[j] < 0 || hg0[j] == a || hg1[j] == a)) { match = false; break; }
@@ -144,6 +172,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 if (!match) continue;
                 // odometer over the complementary allele strings, locus 0 most significant
                 int lo[8], hi_[8], curv[8];
+#pragma unroll 1
                 for (int j = 0; j < head_len; ++j) {
                     const int a = ha[j];
                     const bool both = hg0[j] < 0 && hg1[j] < 0, any = hg0[j] < 0 || hg1[j] < 0;
@@ -155,6 +184,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 for (;;) {
                     bool ok = true;
                     int code = 0;
+#pragma unroll 1
                     for (int j = 0; j < head_len; ++j) {
                         if (lo[j] != hi_[j] && !(((pn.linfo[j] >> 8) >> curv[j]) & 1u)) ok = false;
                         code += curv[j] * md.head_stride[j];
@@ -234,7 +264,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             else if (g0 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g1); }
             else if (g1 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g0); }
             else add_group(g0, g1);
-            if (tid == 0) { sm.gbase[ng] = C; sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; }
+            if (tid == 0) { sm.gbase[ng] = C; sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; sm.ints[7] = 0; }
             if (tid < 8) sm.look[tid] = 0;
             int hsize = 64;
             while (hsize * 4 < 5 * C) hsize <<= 1;     // load factor <= 0.8 even if every candidate were a new state
@@ -250,21 +280,21 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             long long new_off = 0;
 
             // The step body; FAST selects shared-memory work arrays (compile-time, so the accesses are LDS/STS/ATOMS).
-            // returns 0 = ok, 1 = every extension died, 2 = status set (the hash arrays were reset)
+            // returns 0 = ok, 1 = every extension died, 2 = status set (the hash slots were reset)
             auto body = [&](auto fast_tag) -> int {
                 constexpr bool FAST = decltype(fast_tag)::value;
-                u64 *const keys = FAST ? sm.keys : sc.keys;
-                double *const tpvs = FAST ? sm.tpv : sc.tpv;
-                u32 *const ord = FAST ? sm.ord : sc.ord;
-                u32 *const cnt = FAST ? sm.cnt : sc.cnt;
-                u32 *const soff = FAST ? sm.soff : sc.soff;
+                HashTab tab;
+                tab.keys = FAST ? sm.keys : sc.keys; tab.tpvs = FAST ? sm.tpv : sc.tpv; tab.ord = FAST ? sm.ord : sc.ord;
+                tab.cnt = FAST ? sm.cnt : sc.cnt; tab.soffs = FAST ? sm.soff : sc.soff;
                 int *const cand = FAST ? sm.cand : sc.cand;
                 int *const sarr = FAST ? sm.sarr : sc.sarr;
                 int2 *const mlist = FAST ? sm.mlist : sc.mlist;
+                const int mcap = FAST ? (CC / 2 + 1) : sc.scap;
                 const u32 hmask = (u32) hsize - 1u;
-                auto reset_table = [&]() {      // error exits: leave the hash arrays all-empty for the next individual
+                auto reset_table = [&]() {      // error exits: leave the hash slots all-empty for the next individual
                     block_sync<NT>();
-                    for (int h = tid; h < hsize; h += NT) { keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0; }
+#pragma unroll 1
+                    for (int h = tid; h < hsize; h += NT) tab.release((u32) h);
                 };
 
                 // input state views
@@ -273,8 +303,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 const double *gi_alpha = (const double *) (arena + cur_off + bli.alpha);
                 const double *gi_v1 = (const double *) (arena + cur_off + bli.v1);
                 const bool in_cache = FAST || S_in <= CC;       // FAST implies S_in <= C <= CC
-                const int *ci_ida = sm.ida[par], *ci_idb = sm.idb[par];
-                const double *ci_alpha = sm.alpha[par], *ci_v1 = sm.v1[par];
+                const int *const in_ida = in_cache ? sm.ida[par] : gi_ida, *const in_idb = in_cache ? sm.idb[par] : gi_idb;
+                const double *const in_alpha = in_cache ? sm.alpha[par] : gi_alpha, *const in_v1 = in_cache ? sm.v1[par] : gi_v1;
 
                 // forward-link block of index i (E-step mode)
                 long long fwd_off = 0;
@@ -283,7 +313,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 PASS_MARK(0);
                 if (estep) {
                     fwd_off = sm.ll[1];
-                    if (fwd_off < 0) { status = ST_NOMEM; return 2; }       // nothing inserted yet: the hash arrays are clean
+                    if (fwd_off < 0) { status = ST_NOMEM; return 2; }       // nothing inserted yet: the hash slots are clean
                     if (tid == 0) { rec[i].fwd_off = fwd_off; rec[i].fwd_slots = C; }
                 }
                 int *fwd = (int *) (arena + fwd_off);
@@ -297,71 +327,66 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
                 // ---- pass A: lanes over predecessor states; gather successors, canonicalise, hash-insert ----
                 int my_new = 0, my_arr = 0;
-                for (int s = tid; s < S_in; s += NT) {
-                    const int pa = in_cache ? ci_ida[s] : gi_ida[s], pb = in_cache ? ci_idb[s] : gi_idb[s];
-                    const double al = in_cache ? ci_alpha[s] : gi_alpha[s];
-                    const bool alive = al > 0.0;       // HaploBuilder.cpp:237
-                    const int4 *ra = succ16 + (size_t) pa * A, *rb = succ16 + (size_t) pb * A;
-                    int4 ea0 = make_int4(-1, 0, 0, 0), ea1 = ea0, eb0 = ea0, eb1 = ea0;
-                    if (alive && A == 2) {      // biallelic: both entries of a row share one 32-byte sector
-                        ea0 = __ldcg(ra); ea1 = __ldcg(ra + 1); eb0 = __ldcg(rb); eb1 = __ldcg(rb + 1);
-                    }
-                    for (int g = 0; g < ng; ++g) {
-                        const int x = sm.gx[g], y = sm.gy[g];
-                        const bool het = x != y;
-                        const int c0 = sm.gbase[g] + (het ? 2 * s : s);
-                        const int nd = het ? 2 : 1;
-                        int4 ea[2], eb[2];
-                        ea[0] = ea[1] = eb[0] = eb[1] = make_int4(-1, 0, 0, 0);
-                        if (alive) {
-                            if (A == 2) {
-                                ea[0] = x ? ea1 : ea0; eb[0] = y ? eb1 : eb0;
-                                ea[1] = y ? ea1 : ea0; eb[1] = x ? eb1 : eb0;
-                            }
-                            else {
+                {
+                    int nx_pa = 0, nx_pb = 0;
+                    double nx_al = 0.0;
+                    if (tid < S_in) { nx_pa = in_ida[tid]; nx_pb = in_idb[tid]; nx_al = in_alpha[tid]; }
+                    for (int s = tid; s < S_in; s += NT) {
+                        const int pa = nx_pa, pb = nx_pb;
+                        const bool alive = nx_al > 0.0;       // HaploBuilder.cpp:237
+                        if (s + NT < S_in) { nx_pa = in_ida[s + NT]; nx_pb = in_idb[s + NT]; nx_al = in_alpha[s + NT]; }      // next round's state, one round ahead
+                        const int4 *ra = succ16 + (size_t) pa * A, *rb = succ16 + (size_t) pb * A;
+                        for (int g = 0; g < ng; ++g) {
+                            const int x = sm.gx[g], y = sm.gy[g];
+                            const bool het = x != y;
+                            const int c0 = sm.gbase[g] + (het ? 2 * s : s);
+                            const int nd = het ? 2 : 1;
+                            int4 ea[2], eb[2];
+                            ea[0] = ea[1] = eb[0] = eb[1] = make_int4(-1, 0, 0, 0);
+                            if (alive) {        // L2 only: the successor table would only evict the hash / segment arrays from L1
                                 ea[0] = __ldcg(ra + x); eb[0] = __ldcg(rb + y);
                                 if (het) { ea[1] = __ldcg(ra + y); eb[1] = __ldcg(rb + x); }
                             }
-                        }
-                        // both orientations: keys first, then the two compare-and-swaps in flight together
-                        u64 key[2];
-                        u32 hh[2], rev[2];
-                        double tv[2];
-                        bool ok[2];
-                        u64 prev[2];
+                            // both orientations: keys first, then the two compare-and-swaps in flight together
+                            u64 key[2];
+                            u32 hh[2], rev[2];
+                            double tv[2];
+                            bool ok[2];
+                            u64 prev[2];
 #pragma unroll
-                        for (int d = 0; d < 2; ++d) {
-                            ok[d] = alive && d < nd && ea[d].x >= 0 && eb[d].x >= 0;
-                            key[d] = 0; hh[d] = 0; rev[d] = 0; tv[d] = 0.0; prev[d] = 0;
-                            if (ok[d]) {
-                                int hpa = ea[d].x, hpb = eb[d].x;
-                                tv[d] = __dmul_rn(__hiloint2double(ea[d].w, ea[d].z), __hiloint2double(eb[d].w, eb[d].z));
-                                if (hpa > hpb) { const int t = hpa; hpa = hpb; hpb = t; rev[d] = 1; }
-                                key[d] = ((u64) (u32) hpa << 32) | (u32) hpb;
-                                hh[d] = mix64(key[d]) & hmask;
-                                prev[d] = atomicCAS(keys + hh[d], KEY_EMPTY, key[d]);
-                            }
-                        }
-#pragma unroll
-                        for (int d = 0; d < 2; ++d) {
-                            if (d >= nd) continue;
-                            int enc = -1;
-                            if (ok[d]) {
-                                u32 h = hh[d];
-                                u64 pv = prev[d];
-                                for (;;) {
-                                    if (pv == KEY_EMPTY) { tpvs[h] = tv[d]; ++my_new; break; }
-                                    if (pv == key[d]) break;
-                                    h = (h + 1) & hmask;
-                                    pv = atomicCAS(keys + h, KEY_EMPTY, key[d]);
+                            for (int d = 0; d < 2; ++d) {
+                                ok[d] = alive && d < nd && ea[d].x >= 0 && eb[d].x >= 0;
+                                key[d] = 0; hh[d] = 0; rev[d] = 0; tv[d] = 0.0; prev[d] = 0;
+                                if (ok[d]) {
+                                    int hpa = ea[d].x, hpb = eb[d].x;
+                                    tv[d] = __dmul_rn(__hiloint2double(ea[d].w, ea[d].z), __hiloint2double(eb[d].w, eb[d].z));
+                                    if (hpa > hpb) { const int t = hpa; hpa = hpb; hpb = t; rev[d] = 1; }
+                                    key[d] = ((u64) (u32) hpa << 32) | (u32) hpb;
+                                    hh[d] = mix64(key[d]) & hmask;
+                                    prev[d] = atomicCAS(tab.keys + hh[d], KEY_EMPTY, key[d]);
                                 }
-                                atomicMin(ord + h, (u32) (c0 + d));
-                                atomicAdd(cnt + h, 1u);
-                                ++my_arr;
-                                enc = (int) (h | (rev[d] << 30));
                             }
-                            cand[c0 + d] = enc;
-                            if (estep && enc < 0) fwd[c0 + d] = -1;
+#pragma unroll
+                            for (int d = 0; d < 2; ++d) {
+                                if (d >= nd) continue;
+                                int enc = -1;
+                                if (ok[d]) {
+                                    u32 h = hh[d];
+                                    u64 pv = prev[d];
+                                    for (;;) {
+                                        if (pv == KEY_EMPTY) { tab.tpvs[h] = tv[d]; ++my_new; break; }
+                                        if (pv == key[d]) break;
+                                        h = (h + 1) & hmask;
+                                        pv = atomicCAS(tab.keys + h, KEY_EMPTY, key[d]);
+                                    }
+                                    atomicMin(tab.ord + h, (u32) (c0 + d));
+                                    atomicAdd(tab.cnt + h, 1u);
+                                    ++my_arr;
+                                    enc = (int) (h | (rev[d] << 30));
+                                }
+                                cand[c0 + d] = enc;
+                                if (estep && enc < 0) fwd[c0 + d] = -1;
+                            }
                         }
                     }
                 }
@@ -396,27 +421,33 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 if (!estep && tid == 0) t_aoff[S_out] = n_arr;
 
                 // ---- pass C: creators in ordinal order -> state indices and arrival offsets; single-arrival states are finished here ----
+                // a lane owns 4 consecutive ordinals of a 128-candidate tile: the slot loads of a tile are 4-deep per lane and one look-back serves 128
                 {
                     const int ntiles = (C + 127) >> 7;
                     for (int tile = wid; tile < ntiles; tile += NW) {
                         const int c0 = (tile << 7) + lane * 4;
-                        int enc[4], nn[4];
-                        bool cr[4];
-                        u32 ov[4];
+                        int enc[4];
                         if (c0 + 4 <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
                         else {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) ov[u] = enc[u] >= 0 ? ord[enc[u] & SLOT_MASK] : 0xFFFFFFFFu;
-                        int ncr = 0, nar = 0;
+                        // the slot of every candidate: four independent loads each, one trip
+                        u64 skey[4];
+                        double stv[4];
+                        u32 sord[4], scnt[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            cr[u] = enc[u] >= 0 && ov[u] == (u32) (c0 + u);
-                            nn[u] = cr[u] ? (int) cnt[enc[u] & SLOT_MASK] : 0;
+                            skey[u] = 0; stv[u] = 0.0; sord[u] = 0xFFFFFFFFu; scnt[u] = 0;
+                            if (enc[u] >= 0) { const u32 h = (u32) enc[u] & SLOT_MASK; sord[u] = tab.ord[h]; scnt[u] = tab.cnt[h]; skey[u] = tab.keys[h]; stv[u] = tab.tpvs[h]; }
+                        }
+                        int ncr = 0, nar = 0;
+                        bool cr[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            cr[u] = enc[u] >= 0 && sord[u] == (u32) (c0 + u);
                             ncr += cr[u] ? 1 : 0;
-                            nar += nn[u];
+                            nar += cr[u] ? (int) scnt[u] : 0;
                         }
                         int xs = ncr, xa = nar;
 #pragma unroll
@@ -445,50 +476,48 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             const int c = c0 + u;
                             const u32 h = (u32) enc[u] & SLOT_MASK;
                             const u32 rev = ((u32) enc[u] >> 30) & 1u;
-                            const u64 key = keys[h];
-                            const double tv = tpvs[h];
+                            const u64 key = skey[u];
+                            const double tv = stv[u];
+                            const int nn = (int) scnt[u];
                             int g, s, dir;
                             decode(c, g, s, dir);
                             const int gxv = sm.gx[g], gyv = sm.gy[g];
                             const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
                             const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
-                            t_ida[idx] = hpa; t_idb[idx] = hpb;
-                            t_ab[idx] = (unsigned char) ((rev ? yy : xx) | ((rev ? xx : yy) << 4));
-                            if (estep) t_tp[idx] = tv; else t_aoff[idx] = off;
+                            ST_OUT(t_ida + idx, hpa); ST_OUT(t_idb + idx, hpb);
+                            ST_OUT(t_ab + idx, (unsigned char) ((rev ? yy : xx) | ((rev ? xx : yy) << 4)));
+                            if (estep) ST_OUT(t_tp + idx, tv); else ST_OUT(t_aoff + idx, off);
                             if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; }
-                            if (nn[u] == 1) {
-                                const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
-                                const double alpha = __dmul_rn(ain, tv);
-                                t_alpha[idx] = alpha;
+                            if (nn == 1) {
+                                const double alpha = __dmul_rn(in_alpha[s], tv);
+                                ST_OUT(t_alpha + idx, alpha);
                                 if (out_cache) co_alpha[idx] = alpha;
                                 amax = fmax(amax, alpha);
                                 if (!estep) {
-                                    const double v = __dmul_rn(in_cache ? ci_v1[s] : gi_v1[s], tv);
-                                    t_v1[idx] = v;
+                                    const double v = __dmul_rn(in_v1[s], tv);
+                                    ST_OUT(t_v1 + idx, v);
                                     if (out_cache) co_v1[idx] = v;
-                                    t_arr[off] = (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u);
+                                    ST_OUT(t_arr + off, (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u));
                                 }
                                 else fwd[c] = (int) ((u32) idx | (rev << 31));
-                                keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0;
+                                tab.release(h);
                                 cand[c] = -1;
                             }
                             else {
-                                ord[h] = 0x80000000u | (u32) idx;     // never equals an ordinal
-                                cnt[h] = 0;
-                                soff[h] = (u32) off;
-                                const int m = atomicAdd(&sm.ints[6], 1);
-                                mlist[m] = make_int2(idx, (int) h);
+                                tab.created(h, (u32) idx, (u32) off);     // ord = state index (never equals an ordinal), cnt = 0 (the scatter counts again), soff
+                                if (nn <= 8) mlist[atomicAdd(&sm.ints[6], 1)] = make_int2(idx, (int) h);
+                                else mlist[mcap - 1 - atomicAdd(&sm.ints[7], 1)] = make_int2(idx, (int) h);
                             }
-                            ++idx; off += nn[u];
+                            ++idx; off += nn;
                         }
                     }
                 }
                 block_sync<NT>();
                 PASS_MARK(2);
-                const int n_multi = sm.ints[6];
+                const int n_light = sm.ints[6], n_heavy = sm.ints[7];
 
-                // ---- pass D: scatter the arrivals of multi-arrival states (unordered inside a segment; sorted in E) ----
-                if (n_multi > 0) {
+                // ---- pass D: scatter the arrivals of multi-arrival states (unordered inside a segment; ordered in E) ----
+                if (n_light + n_heavy > 0) {
                     for (int base = 0; base < C; base += NT * 4) {
                         const int c0 = base + tid * 4;
                         int enc[4];
@@ -503,9 +532,9 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             so[u] = 0; pos[u] = 0; ov[u] = 0;
                             if (enc[u] >= 0) {
                                 const u32 h = (u32) enc[u] & SLOT_MASK;
-                                so[u] = soff[h];
-                                pos[u] = atomicAdd(cnt + h, 1u);
-                                if (estep) ov[u] = ord[h];
+                                so[u] = tab.soffs[h];
+                                pos[u] = atomicAdd(tab.cnt + h, 1u);
+                                if (estep) ov[u] = tab.ord[h];
                             }
                         }
 #pragma unroll
@@ -521,62 +550,102 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 }
                 PASS_MARK(3);
 
-                // ---- pass E: one lane per multi-arrival state ----
-                for (int m = tid; m < n_multi; m += NT) {
+                // ---- pass E (light): one lane per state with 2..8 arrivals, ordered in registers ----
+                for (int m = tid; m < n_light; m += NT) {
                     const int2 me = mlist[m];
                     const int idx = me.x;
                     const u32 h = (u32) me.y;
-                    const double tv = tpvs[h];
-                    const int a0 = (int) soff[h], n = (int) cnt[h];
-                    keys[h] = KEY_EMPTY; ord[h] = 0xFFFFFFFFu; cnt[h] = 0;
+                    const double tv = tab.tpvs[h];
+                    const int a0 = (int) tab.soffs[h], n = (int) tab.cnt[h];
+                    tab.release(h);
+                    int v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = (q < n) ? sarr[a0 + q] : 0x7FFFFFFF;
+                    auto cx = [&](int a, int b) { const int x = v[a], y = v[b]; const bool sw = (x & 0x7FFFFFFF) > (y & 0x7FFFFFFF); v[a] = sw ? y : x; v[b] = sw ? x : y; };
+                    if (n > 2) {        // 19-comparator network for 8 (padding sorts to the end)
+                        cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
+                        cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
+                        cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
+                        cx(1, 5); cx(2, 6);
+                        cx(1, 4); cx(3, 6);
+                        cx(2, 4); cx(3, 5);
+                        cx(3, 4);
+                    }
+                    else cx(0, 1);
                     double alpha = 0.0, vmax = 0.0;
-                    auto take = [&](int e, int j) {
-                        int g, s, dir;
-                        decode(e & 0x7FFFFFFF, g, s, dir);
-                        const double ain = in_cache ? ci_alpha[s] : gi_alpha[s];
-                        const double term = __dmul_rn(ain, tv);
-                        alpha = (j == 0) ? term : __dadd_rn(alpha, term);
-                        if (!estep) {
-                            vmax = fmax(vmax, in_cache ? ci_v1[s] : gi_v1[s]);
-                            t_arr[a0 + j] = (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u);
-                        }
-                    };
-                    if (n <= 8) {
-                        // ordinal order inside the segment: up to 8 arrivals are sorted in registers (19-comparator network)
-                        int v[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = (q < n) ? sarr[a0 + q] : 0x7FFFFFFF;
-                        auto cx = [&](int a, int b) { const int x = v[a], y = v[b]; const bool sw = (x & 0x7FFFFFFF) > (y & 0x7FFFFFFF); v[a] = sw ? y : x; v[b] = sw ? x : y; };
-                        if (n > 2) {
-                            cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
-                            cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
-                            cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
-                            cx(1, 5); cx(2, 6);
-                            cx(1, 4); cx(3, 6);
-                            cx(2, 4); cx(3, 5);
-                            cx(3, 4);
+                    for (int q = 0; q < 8; ++q) {
+                        if (q < n) {
+                            int g, s, dir;
+                            decode(v[q] & 0x7FFFFFFF, g, s, dir);
+                            const double term = __dmul_rn(in_alpha[s], tv);
+                            alpha = (q == 0) ? term : __dadd_rn(alpha, term);
+                            if (!estep) {
+                                vmax = fmax(vmax, in_v1[s]);
+                                ST_OUT(t_arr + a0 + q, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) v[q] >> 31) ? ARR_REV : 0u));
+                            }
                         }
-                        else cx(0, 1);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) if (q < n) take(v[q], q);
                     }
-                    else {
-                        for (int j = 1; j < n; ++j) {
-                            const int e = sarr[a0 + j];
-                            int q = j - 1;
-                            while (q >= 0 && (sarr[a0 + q] & 0x7FFFFFFF) > (e & 0x7FFFFFFF)) { sarr[a0 + q + 1] = sarr[a0 + q]; --q; }
-                            sarr[a0 + q + 1] = e;
-                        }
-                        for (int j = 0; j < n; ++j) take(sarr[a0 + j], j);
-                    }
-                    t_alpha[idx] = alpha;
+                    ST_OUT(t_alpha + idx, alpha);
                     if (out_cache) co_alpha[idx] = alpha;
                     amax = fmax(amax, alpha);
                     if (!estep) {
-                        const double v = __dmul_rn(vmax, tv);       // = max over arrivals of v1(pred) * tp: rounding is monotone
-                        t_v1[idx] = v;
-                        if (out_cache) co_v1[idx] = v;
+                        const double vv = __dmul_rn(vmax, tv);       // = max over arrivals of v1(pred) * tp: rounding is monotone
+                        ST_OUT(t_v1 + idx, vv);
+                        if (out_cache) co_v1[idx] = vv;
                     }
+                }
+                // ---- pass E (heavy): one warp per state with more than 8 arrivals (about 1 % of the states); rank by counting, ordered copy in `cand` (free after D) ----
+                for (int m = wid; m < n_heavy; m += NW) {
+                    const int2 me = mlist[mcap - 1 - m];
+                    const int idx = me.x;
+                    const u32 h = (u32) me.y;
+                    const double tv = tab.tpvs[h];
+                    const int a0 = (int) tab.soffs[h], n = (int) tab.cnt[h];
+                    __syncwarp();
+                    if (lane == 0) tab.release(h);
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        const int mine = (b0 + lane < n) ? sarr[a0 + b0 + lane] : 0x7FFFFFFF;
+                        int rank = 0;
+                        for (int q0 = 0; q0 < n; q0 += 32) {
+                            const int other = (q0 + lane < n) ? sarr[a0 + q0 + lane] : 0x7FFFFFFF;
+                            const int lim = min(32, n - q0);
+                            for (int j = 0; j < lim; ++j) rank += ((__shfl_sync(FULL, other, j) & 0x7FFFFFFF) < (mine & 0x7FFFFFFF)) ? 1 : 0;
+                        }
+                        if (b0 + lane < n) cand[a0 + rank] = mine;
+                    }
+                    __syncwarp();
+                    double alpha = 0.0, vmax = 0.0;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        double term = 0.0;
+                        if (b0 + lane < n) {
+                            const int e = cand[a0 + b0 + lane];
+                            int g, s, dir;
+                            decode(e & 0x7FFFFFFF, g, s, dir);
+                            term = __dmul_rn(in_alpha[s], tv);
+                            if (!estep) {
+                                vmax = fmax(vmax, in_v1[s]);
+                                ST_OUT(t_arr + a0 + b0 + lane, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
+                            }
+                        }
+                        const int lim = min(32, n - b0);
+                        for (int j = 0; j < lim; ++j) {
+                            const double tj = __shfl_sync(FULL, term, j);
+                            alpha = (b0 + j == 0) ? tj : __dadd_rn(alpha, tj);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(FULL, vmax, o));
+                    if (lane == 0) {
+                        ST_OUT(t_alpha + idx, alpha);
+                        if (out_cache) co_alpha[idx] = alpha;
+                        if (!estep) {
+                            const double vv = __dmul_rn(vmax, tv);
+                            ST_OUT(t_v1 + idx, vv);
+                            if (out_cache) co_v1[idx] = vv;
+                        }
+                    }
+                    amax = fmax(amax, alpha);
                 }
                 PASS_MARK(4);
                 if (p.scaled) {     // exponent-only rescale: mantissas stay those of the unscaled product

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libhmc_b200.so")
+_SO = os.environ.get("HMC_B200_LIB") or os.path.join(_HERE, "libhmc_b200.so")     # (the override is for kernel experiments)
 _LIB = None
 
 FLAG_SCALED = 1

@@ -13,8 +13,9 @@ g = make_panel(N, L, founders=16, missing=miss, seed=2)
 hm = HaploModel(); hm.set_panel(g, "S"); t = time.time(); hm.build(); m = hm.export_model(); print("build %.1fs P=%d" % (time.time() - t, m["P"]), flush=True)
 idx, na, af = hm.panel()
 dev = DeviceBuilder(threads=nt); dev.set_panel(idx, na, af); dev.set_model(m)
-dev.resolve_all_device(K=K)
-dev.resolve_all_device(K=K)
+cnt = int(os.environ.get('COUNT', N))
+dev.resolve_all_device(K=K, count=cnt)
+dev.resolve_all_device(K=K, count=cnt)
 ms = dev.kernel_ms(); c = dev.counters()
 print(f"K={K} nt={nt}: fwd {ms['forward']:.2f} ms tb {ms['traceback']:.2f} ms {c}", flush=True)
 d = np.zeros((N, 8), np.int64); inds = np.zeros(N, np.int32)

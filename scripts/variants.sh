@@ -1,1 +1,5 @@
-for v in 4 5 6; do echo "K4 MINB $v"; HMC_B200_K4_MINB=$v python scripts/probe_c2.py 2000 1000 0.05 4 128 2>&1 | tail -1; done
+#!/bin/bash
+# usage: variants.sh "<probe args>" lib1.so lib2.so ...   (libraries relative to the repo root)
+cd $GRAFT_REPO_ROOT
+args=$1; shift
+for lib in "$@"; do echo "== $lib"; HMC_B200_LIB=$GRAFT_REPO_ROOT/$lib python scripts/probe_c2.py $args 2>&1 | grep "K="; done
