@@ -26,9 +26,6 @@
 
 using namespace hmc;
 
-#ifndef FWD_MINB_128
-#define FWD_MINB_128 6
-#endif
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -258,8 +255,8 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
 #ifdef FWD_SWEEP
     if (const char *env = getenv("HMC_B200_FWD_CFG")) {     // kernel-configuration experiments
         switch (atoi(env)) {
-            case 0: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
-            case 1: return launch_forward_t<256, 256, 4>(p, grid, st, occ);
+            case 0: return launch_forward_t<128, 256, 6>(p, grid, st, occ);
+            case 1: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
             case 2: return launch_forward_t<256, 512, 2>(p, grid, st, occ);
             case 3: return launch_forward_t<256, 1024, 2>(p, grid, st, occ);
             case 4: return launch_forward_t<512, 512, 2>(p, grid, st, occ);
@@ -271,11 +268,13 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
         }
     }
 #endif
+    // measured on C2 (profiles/README.md, round 2): 256 threads per individual with 4 resident CTAs per SM is the best of the swept
+    // configurations; beyond ~16-24 resident warps per SM more CTAs only add L2 / DRAM traffic of their spill scratch
     switch (nt) {
         case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
         case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
-        case 256: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
-        default: return launch_forward_t<128, 256, FWD_MINB_128>(p, grid, st, occ);
+        case 128: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
+        default: return launch_forward_t<256, 256, 4>(p, grid, st, occ);
     }
 }
 
@@ -329,8 +328,8 @@ static int pick_threads(const hmc_ctx *ctx)
 {
     const char *env = getenv("HMC_B200_THREADS");
     int nt = ctx->threads_opt > 0 ? ctx->threads_opt : (env ? atoi(env) : 0);
-    if (nt == 0) nt = 128;
-    if (nt != 32 && nt != 64 && nt != 128 && nt != 256) nt = 128;
+    if (nt == 0) nt = 256;
+    if (nt != 32 && nt != 64 && nt != 128 && nt != 256) nt = 256;
     return nt;
 }
 

@@ -412,15 +412,6 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
             }
             __syncwarp();
         };
-        auto ensure = [&](u32 ref, int j) {     // list(ref) gets more than j links unless it runs out
-            for (;;) {
-                __syncwarp();
-                KbNode nd = node_at(ref);
-                if ((int) nd.nD() > j || nd.exhausted() || nomem) return;
-                lazy_next(ref);
-            }
-        };
-
         if (base == L) {
             // every index is eager (no typed heterozygous locus before the last index): selection over all final links, x2 unless homozygous
             const EagerLayout el = eager_layout(S_fin, K);
@@ -477,39 +468,54 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
         }
         if (!p.haps) continue;
 
-        // ---- the paths (HaploPair::getGenotype): warp-uniform walk, 32 loci buffered across the lanes per flush ----
-        for (int r = 0; r < n_sel && !nomem; ++r) {
-            signed char *out = p.haps + ((size_t) row * K + r) * 2 * L;
+        // ---- the paths (HaploPair::getGenotype): lane r walks path r.  Links with a node behind them are read from the node; a link
+        // whose predecessor was never expanded is the predecessor's best link (index 0), found from the trellis directly with the
+        // same (value, arrival order) rule the enumeration uses ----
+        __syncwarp();
+        if (lane < n_sel) {
+            signed char *out = p.haps + ((size_t) row * K + lane) * 2 * L;
             int level = L, state = 0, k = 0;
             int a = 0;          // which output row currently plays pattern_a's role
-            signed char r0 = 0, r1 = 0;
-            auto emit = [&](int locus, int al_a, int al_b) {
-                if (lane == (locus & 31)) { r0 = (signed char) (a ? al_b : al_a); r1 = (signed char) (a ? al_a : al_b); }
-                if ((locus & 31) == 0) {
-                    if (locus + lane < L) { out[locus + lane] = r0; out[(size_t) L + locus + lane] = r1; }
-                }
-            };
             if (base < L) {
                 KbNode rn = node_at(root);
-                u32 bp = rn.dbp()[r];
-                u32 ref = rn.dnode()[r];
+                u32 bp = rn.dbp()[lane];
+                u32 ref = rn.dnode()[lane];
                 state = (int) (bp & ARR_PRED_MASK); k = (int) ((bp >> BP_PRED_BITS) & 31u);
                 for (; level > base; --level) {
-                    if (!ref) { ref = find_or_create(level, state); if (!ref) break; }
-                    ensure(ref, k);
-                    if (nomem) break;
-                    KbNode nd = node_at(ref);
-                    const unsigned char ab = ((const unsigned char *) (blk_of(level) + lay_of(level).ab))[state];
-                    emit(level - 1, ab & 15, ab >> 4);
-                    bp = nd.dbp()[k];
-                    ref = nd.dnode()[k];
+                    const BlockLayout b = lay_of(level);
+                    const u64 *blk = blk_of(level);
+                    const unsigned char ab = ((const unsigned char *) (blk + b.ab))[state];
+                    out[(size_t) a * L + level - 1] = (signed char) (ab & 15);
+                    out[(size_t) (a ^ 1) * L + level - 1] = (signed char) (ab >> 4);
+                    if (ref) {
+                        KbNode nd = node_at(ref);
+                        bp = nd.dbp()[k];
+                        ref = nd.dnode()[k];
+                    }
+                    else {      // best link of (level, state)
+                        const int ia = ((const int *) (blk + b.ida))[state], ib = ((const int *) (blk + b.idb))[state];
+                        const double tpv = __dmul_rn(md.tp[ia], md.tp[ib]);
+                        const double fac = fac_of(level);
+                        const int *aoff = (const int *) (blk + b.aoff);
+                        const int a0 = aoff[state], a1 = aoff[state + 1];
+                        const u32 *arr = (const u32 *) (blk + b.arr);
+                        const double *pv1 = (const double *) (blk_of(level - 1) + lay_of(level - 1).v1);
+                        double bv = -1.0;
+                        u32 bw = 0;
+                        for (int e = a0; e < a1; ++e) {
+                            const u32 wd = arr[e];
+                            double v = __dmul_rn(pv1[wd & ARR_PRED_MASK], tpv);
+                            if (fac != 1.0) v *= fac;
+                            if (v > bv) { bv = v; bw = wd; }
+                        }
+                        bp = (bw & ARR_PRED_MASK) | ((bw & ARR_REV) ? BP_REV : 0u);
+                    }
                     if (bp & BP_REV) a ^= 1;
                     state = (int) (bp & ARR_PRED_MASK); k = (int) ((bp >> BP_PRED_BITS) & 31u);
                 }
-                if (nomem) break;
             }
             else {
-                const int e = (int) stack[r];
+                const int e = (int) stack[lane];
                 state = e / K; k = e - state * K;
             }
             // eager indices: back-pointer words of the eager lists down to the head
@@ -521,16 +527,17 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
                 if (bp & BP_HEAD) {
                     const int ia = ((const int *) (blk + b.ida))[state], ib = ((const int *) (blk + b.idb))[state];
                     const signed char *pa = md.al + md.al_off[ia], *pb = md.al + md.al_off[ib];
-                    for (int q = level - 1; q >= 0; --q) emit(q, pa[q], pb[q]);
+                    for (int q = 0; q < level; ++q) { out[(size_t) a * L + q] = pa[q]; out[(size_t) (a ^ 1) * L + q] = pb[q]; }
                     break;
                 }
                 const unsigned char ab = ((const unsigned char *) (blk + b.ab))[state];
-                emit(level - 1, ab & 15, ab >> 4);
+                out[(size_t) a * L + level - 1] = (signed char) (ab & 15);
+                out[(size_t) (a ^ 1) * L + level - 1] = (signed char) (ab >> 4);
                 if (bp & BP_REV) a ^= 1;
                 state = (int) (bp & ARR_PRED_MASK); k = (int) ((bp >> BP_PRED_BITS) & 31u);
             }
         }
-        if (nomem) { if (lane == 0) p.status[w] = ST_NOMEM_KBEST; continue; }
+        __syncwarp();
     }
     if (lane == 0) { atomicAdd(p.work + 0, n_next); atomicAdd(p.work + 1, n_nodes); atomicAdd(p.work + 2, n_eager); }
 }
