@@ -474,6 +474,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
     ctx->kb_work[0] = hc[24]; ctx->kb_work[1] = hc[25]; ctx->kb_work[2] = hc[26];
+    if (getenv("HMC_B200_PRINT_KBEST")) fprintf(stderr, "kbest: %lld lazy-next visits, %lld nodes, %lld eager-list states\n", hc[24], hc[25], hc[26]);
     ctx->last_K = K; ctx->last_estep = estep;
     if (estep && waves == 1) {
         ctx->ecache.first = first; ctx->ecache.count = count; ctx->ecache.flags = flags; ctx->ecache.fp = fp; ctx->ecache.n_wave = fp.n_wave;

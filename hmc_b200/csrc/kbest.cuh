@@ -317,7 +317,19 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
                            if (lane == 0) { nd.head()[r] = v; nd.sword()[r] = word_of(e); nd.snode()[r] = 0; nd.sj()[r] = 0; }
                            ns = r + 1;
                        });
-            if (lane == 0) { nd.tpv() = tpv; nd.fac() = fac; nd.nS() = (unsigned char) ns; }
+            if (lane == 0) {
+                nd.tpv() = tpv; nd.fac() = fac; nd.nS() = (unsigned char) ns;
+                if (ns > 0) {       // the first link is the best head: stream 0 (select_top emits best first)
+                    const u32 sw = nd.sword()[0];
+                    nd.dv()[0] = nd.head()[0];
+                    nd.dbp()[0] = (sw & ARR_PRED_MASK) | ((sw & ARR_REV) ? BP_REV : 0u);
+                    nd.dnode()[0] = 0;
+                    nd.sj()[0] = 1;
+                    nd.pending() = 0;
+                    nd.nD() = 1;
+                }
+                else nd.exhausted() = 1;
+            }
         };
         auto find_or_create = [&](int level, int state) -> u32 {
             u32 ref = chain[level];
@@ -348,43 +360,51 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
             __syncwarp();
             return ref;
         };
-        // appends one more link to the list of node `top` (or marks it exhausted); nodes below it are advanced as needed
+        // appends one more link to the list of node `top` (or marks it exhausted); nodes below it are advanced as needed.
+        // Per visit the node is read once with the lanes spread over its streams (lane e holds head / arrival word / predecessor node /
+        // next index of stream e), the header by broadcast; updates go back as single stores, nothing is re-read.
         auto lazy_next = [&](u32 top) {
             int sp = 0;
             u32 cur = top;
             for (;;) {
                 __syncwarp();
                 KbNode nd = node_at(cur);
-                const int pend = nd.pending();
+                const uint4 hdr = *reinterpret_cast<const uint4 *>(nd.b);           // level, state, next, {nD, nS, pending, exhausted}
+                const int ns = (int) ((hdr.w >> 8) & 0xFFu), pend = (int) ((hdr.w >> 16) & 0xFFu);
+                int k = (int) (hdr.w & 0xFFu);
+                double my_head = -1.0;
+                u32 my_sw = 0, my_sn = 0;
+                int my_j = 0;
+                if (lane < ns) { my_head = nd.head()[lane]; my_sw = nd.sword()[lane]; my_sn = nd.snode()[lane]; my_j = nd.sj()[lane]; }
                 if (pend != (int) KB_NONE) {
-                    const int j = nd.sj()[pend];
+                    const int j = __shfl_sync(FULL, my_j, pend);
                     double hv = -1.0;
                     if (j < K) {
-                        u32 pref = nd.snode()[pend];
+                        u32 pref = __shfl_sync(FULL, my_sn, pend);
                         if (!pref) {
-                            pref = find_or_create(nd.level() - 1, (int) (nd.sword()[pend] & ARR_PRED_MASK));
+                            pref = find_or_create((int) hdr.x - 1, (int) (__shfl_sync(FULL, my_sw, pend) & ARR_PRED_MASK));
                             if (!pref) return;
-                            if (lane == 0) nd.snode()[pend] = pref;
+                            if (lane == pend) { my_sn = pref; nd.snode()[pend] = pref; }
                         }
                         KbNode pd = node_at(pref);
-                        if ((int) pd.nD() > j) {
-                            hv = __dmul_rn(pd.dv()[j], nd.tpv());
+                        const u32 pw = *reinterpret_cast<const u32 *>(pd.b + 12);
+                        const double pv = pd.dv()[j];           // (read before it is known to be valid: inside the node)
+                        if ((int) (pw & 0xFFu) > j) {
+                            hv = __dmul_rn(pv, nd.tpv());
                             const double fac = nd.fac();
                             if (fac != 1.0) hv *= fac;
                         }
-                        else if (!pd.exhausted()) {     // the predecessor's list has to grow first
+                        else if (!(pw >> 24)) {     // the predecessor's list has to grow first
                             if (lane == 0) stack[sp] = cur;
                             ++sp;
                             cur = pref;
                             continue;
                         }
                     }
-                    if (lane == 0) { nd.head()[pend] = hv; nd.pending() = (unsigned char) KB_NONE; }
-                    __syncwarp();
+                    if (lane == pend) { my_head = hv; nd.head()[pend] = hv; }
                 }
                 // take the best stream head (ties: the earlier stream)
-                const int ns = nd.nS();
-                double bv = lane < ns ? nd.head()[lane] : -1.0;
+                double bv = my_head;
                 int be = lane;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -392,17 +412,15 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
                     const int oe = __shfl_xor_sync(FULL, be, o);
                     if (ov > bv || (ov == bv && oe < be)) { bv = ov; be = oe; }
                 }
-                if (bv < 0.0) { if (lane == 0) nd.exhausted() = 1; }
-                else if (lane == 0) {
-                    const int k = nd.nD();
-                    const int j = nd.sj()[be];
-                    const u32 sw = nd.sword()[be];
-                    nd.dv()[k] = bv;
-                    nd.dbp()[k] = (sw & ARR_PRED_MASK) | ((u32) j << BP_PRED_BITS) | ((sw & ARR_REV) ? BP_REV : 0u);
-                    nd.dnode()[k] = nd.snode()[be];
-                    nd.sj()[be] = (unsigned char) (j + 1);
-                    nd.pending() = (unsigned char) be;
-                    nd.nD() = (unsigned char) (k + 1);
+                if (bv < 0.0) { if (lane == 0) *reinterpret_cast<u32 *>(nd.b + 12) = (hdr.w & 0x0000FFFFu) | (KB_NONE << 16) | (1u << 24); }
+                else {
+                    if (lane == be) {
+                        nd.dv()[k] = bv;
+                        nd.dbp()[k] = (my_sw & ARR_PRED_MASK) | ((u32) my_j << BP_PRED_BITS) | ((my_sw & ARR_REV) ? BP_REV : 0u);
+                        nd.dnode()[k] = my_sn;
+                        nd.sj()[be] = (unsigned char) (my_j + 1);
+                        *reinterpret_cast<u32 *>(nd.b + 12) = (u32) (k + 1) | ((u32) ns << 8) | ((u32) be << 16);       // nD, nS, pending, not exhausted
+                    }
                 }
                 ++n_next;
                 if (sp == 0) break;
@@ -443,7 +461,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
                 init_streams(node_at(root), S_fin, 2.0, 1.0, fv1, [&](int e) -> u32 { return (u32) e; });
                 __syncwarp();
                 for (int r = 0; r < K && !nomem; ++r) {
-                    lazy_next(root);
+                    if (r > 0) lazy_next(root);         // (the first link was taken when the streams were built)
                     KbNode rn = node_at(root);
                     if ((int) rn.nD() <= r) break;
                     n_sel = r + 1;
