@@ -422,7 +422,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             KbParams kp = {};
             kp.panel = fp.panel; kp.model = fp.model; kp.arena = ctx->d_arena.p; kp.capacity = (long long) ctx->d_arena.n; kp.cursor = ctx->d_cursor.p;
             kp.loci = ctx->d_loci.p; kp.wave = ctx->d_wave.p; kp.status = ctx->d_status.p; kp.final_exp = ctx->d_final_exp.p; kp.locus_exp = fp.locus_exp;
-            kp.n_wave = n_wave; kp.K = K; kp.first = first;
+            kp.n_wave = n_wave; kp.K = K; kp.first = (flags & HMC_FLAG_PANEL_ROWS) ? 0 : first;
             kp.eoff = ctx->d_kb_eoff.p; kp.chain = ctx->d_kb_chain.p; kp.stack = ctx->d_kb_stack.p; kp.stack_stride = L + 40;
             kp.queue = ctx->d_flags.p + 1; kp.work = (unsigned long long *) (ctx->d_counters.p + 24);
             kp.pg = ctx->d_pg.p; kp.cov = ctx->d_cov.p; kp.prior = ctx->d_prior.p; kp.post = ctx->d_post.p; kp.exp2 = ctx->d_exp.p; kp.nres = ctx->d_nres.p;
@@ -710,13 +710,15 @@ int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned f
     CK(cudaSetDevice(ctx->device));
     if (count <= 0 || K < 1 || K > HMC_MAX_K) return ctx->fail(HMC_ERR_INVALID, "hmc_resolve_all: bad count/K");
     const int L = ctx->L;
-    CK(ctx->d_pg.ensure(count)); CK(ctx->d_cov.ensure(count)); CK(ctx->d_exp.ensure(count)); CK(ctx->d_nres.ensure(count));
-    CK(ctx->d_prior.ensure((size_t) count * K)); CK(ctx->d_post.ensure((size_t) count * K));
-    CK(ctx->d_haps.ensure((size_t) count * K * 2 * L));
+    const bool panel_rows = (flags & HMC_FLAG_PANEL_ROWS) != 0;
+    const size_t rows = panel_rows ? (size_t) ctx->N : (size_t) count;
+    CK(ctx->d_pg.ensure(rows)); CK(ctx->d_cov.ensure(rows)); CK(ctx->d_exp.ensure(rows)); CK(ctx->d_nres.ensure(rows));
+    CK(ctx->d_prior.ensure(rows * K)); CK(ctx->d_post.ensure(rows * K));
+    CK(ctx->d_haps.ensure(rows * K * 2 * L));
     ctx->r_count = 0;           // fetch / compare / mine_resolved must not see partial results of a failed call
-    ctx->r_first = first; ctx->r_K = K;
+    ctx->r_first = panel_rows ? 0 : first; ctx->r_K = K;
     const int rc = run_waves(ctx, first, count, K, flags, 0, [](const FwdParams &, int, const std::vector<int> &, int &) { return 0; });
-    if (rc == HMC_OK) ctx->r_count = count;
+    if (rc == HMC_OK) ctx->r_count = (int) rows;
     return rc;
 }
 
@@ -747,9 +749,38 @@ int hmc_fetch_results(hmc_ctx *ctx, double *out_pg, int32_t *out_exp, double *ou
     return HMC_OK;
 }
 
+int hmc_result_device_ptrs(hmc_ctx *ctx, void *ptrs[7], int64_t row_bytes[7])
+{
+    if (!ctx || !ptrs || !row_bytes) return HMC_ERR_INVALID;
+    if (ctx->r_count <= 0) return ctx->fail(HMC_ERR_INVALID, "hmc_result_device_ptrs: no resolve results on the device");
+    const int64_t K = ctx->r_K, L = ctx->L;
+    ptrs[0] = ctx->d_pg.p; row_bytes[0] = 8;
+    ptrs[1] = ctx->d_exp.p; row_bytes[1] = 4;
+    ptrs[2] = ctx->d_cov.p; row_bytes[2] = 8;
+    ptrs[3] = ctx->d_nres.p; row_bytes[3] = 4;
+    ptrs[4] = ctx->d_prior.p; row_bytes[4] = 8 * K;
+    ptrs[5] = ctx->d_post.p; row_bytes[5] = 8 * K;
+    ptrs[6] = ctx->d_haps.p; row_bytes[6] = K * 2 * L;
+    return HMC_OK;
+}
+
+int hmc_fetch_counts(hmc_ctx *ctx, int Pc, double *out_freq, double *out_prefix)
+{
+    if (!ctx || Pc <= 0) return HMC_ERR_INVALID;
+    if (ctx->d_counts.n < (size_t) 2 * Pc) return ctx->fail(HMC_ERR_INVALID, "hmc_fetch_counts: no count vector of %d candidates on the device", Pc);
+    CK(cudaSetDevice(ctx->device));
+    if (out_freq) CK(cudaMemcpyAsync(out_freq, ctx->d_counts.p, sizeof(double) * Pc, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_prefix) CK(cudaMemcpyAsync(out_prefix, ctx->d_counts.p + Pc, sizeof(double) * Pc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HMC_OK;
+}
+
+void *hmc_stream(hmc_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+
 int hmc_resolve_all(hmc_ctx *ctx, int first, int count, int K, unsigned flags, double *out_pg, int32_t *out_exp, double *out_cov,
                     int32_t *out_nres, double *out_prior, double *out_post, int8_t *out_haps, double *out_ll)
 {
+    if (flags & HMC_FLAG_PANEL_ROWS) return ctx ? ctx->fail(HMC_ERR_INVALID, "HMC_FLAG_PANEL_ROWS belongs to hmc_resolve_all_device") : HMC_ERR_INVALID;
     int rc = hmc_resolve_all_device(ctx, first, count, K, flags);
     if (rc) return rc;
     return hmc_fetch_results(ctx, out_pg, out_exp, out_cov, out_nres, out_prior, out_post, out_haps, out_ll);

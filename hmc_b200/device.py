@@ -16,13 +16,14 @@ _LIB = None
 
 FLAG_SCALED = 1
 FLAG_KEEP_TRELLIS = 2
+FLAG_PANEL_ROWS = 4
 CNT_NAMES = ("steps", "states", "max_states", "arrivals", "waves", "spill_steps", "launches", "estep_entries")
 
 EXPORTS = [
     "hmc_version", "hmc_ctx_create", "hmc_ctx_destroy", "hmc_last_error", "hmc_set_panel", "hmc_set_model", "hmc_resolve_all",
     "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
     "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims", "hmc_compare", "hmc_set_panel_packed", "hmc_fetch_best_packed",
-    "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats",
+    "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats", "hmc_result_device_ptrs", "hmc_fetch_counts", "hmc_stream",
 ]
 
 
@@ -65,6 +66,10 @@ def lib():
         L.hmc_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.hmc_get_trellis.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
         L.hmc_get_trellis.restype = C.c_longlong
+        L.hmc_result_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmc_fetch_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hmc_stream.restype = C.c_void_p
+        L.hmc_stream.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -141,11 +146,21 @@ class DeviceBuilder:
     def resolve_all_device(self, K: int = 10, first: int = 0, count: int | None = None, flags: int = 0):
         count = self.N - first if count is None else count
         self._ck(lib().hmc_resolve_all_device(self._h, first, count, K, flags))
-        self._last = (count, K)
+        self._last = (self.N if flags & FLAG_PANEL_ROWS else count, K)
 
-    def fetch_results(self, haps: bool = True) -> dict:
+    def result_device_ptrs(self):
+        """[(device pointer, bytes per individual)] of {pg, exp, coverage, nres, prior, posterior, haps} of the last resolve_all_device call."""
+        ptrs = (C.c_void_p * 7)()
+        rb = (C.c_int64 * 7)()
+        self._ck(lib().hmc_result_device_ptrs(self._h, ptrs, rb))
+        return [(int(ptrs[i] or 0), int(rb[i])) for i in range(7)]
+
+    def fetch_results(self, haps: bool = True, out: dict | None = None) -> dict:
         count, K = self._last
-        r = self._alloc(count, K, haps)
+        r = dict(out) if out is not None else self._alloc(count, K, haps)
+        if out is not None:
+            assert r["prior"].shape == (count, K) and r["pg"].shape == (count,)
+            r["ll"] = np.zeros(1)
         self._ck(lib().hmc_fetch_results(self._h, _p(r["pg"]), _p(r["exp"]), _p(r["coverage"]), _p(r["nres"]), _p(r["prior"]),
                                          _p(r["posterior"]), _p(r["haps"]), _p(r["ll"])))
         r["ll"] = float(r["ll"][0])

@@ -63,6 +63,7 @@ class HaploModel:
         if not self._h:
             raise HmcError(err.value.decode())
         self._h = C.c_void_p(self._h)
+        self.device_index = device
         self.opts = dict(self.DEFAULTS)
         self.set_options(**opts)
         self.N = self.L = self.Amax = 0

@@ -921,6 +921,22 @@ void HaploBuilder::resolveAll(int sample_size, ResolveResult &r, bool want_haps)
     r.prior.assign((size_t) N * K, 0); r.posterior.assign((size_t) N * K, 0);
     if (want_haps) r.haps.assign((size_t) N * K * 2 * L, -1); else r.haps.clear();
     double ll_shard = 0;
+    if (count < N && gather_device) {
+        // sharded, exchange on the device: the result block has one row per panel individual, this rank fills its own rows, the
+        // all-gather fills the others in place (7 arrays), and only then the host copies are made -- every rank ends up with every
+        // individual's result and with all K sampled pairs still on its device for the next pattern search
+        if (count > 0) ck(m_ctx, hmc_resolve_all_device(m_ctx, first, count, K, m_flags | HMC_FLAG_PANEL_ROWS), "hmc_resolve_all_device");
+        else ck(m_ctx, hmc_resolve_all_device(m_ctx, 0, 1, K, m_flags | HMC_FLAG_PANEL_ROWS), "hmc_resolve_all_device");      // (a rank without individuals still owns a result block)
+        void *ptrs[7];
+        int64_t row_bytes[7];
+        ck(m_ctx, hmc_result_device_ptrs(m_ctx, ptrs, row_bytes), "hmc_result_device_ptrs");
+        for (int a = 0; a < 7; ++a) gather_device(ptrs[a], (size_t) row_bytes[a]);
+        ck(m_ctx, hmc_fetch_results(m_ctx, r.pg.data(), r.exp2.data(), r.coverage.data(), r.nres.data(), r.prior.data(), r.posterior.data(),
+                                    want_haps ? r.haps.data() : nullptr, nullptr), "hmc_fetch_results");
+        r.ll = 0;
+        for (int i = 0; i < N; ++i) r.ll += r.exp2[i] ? (std::log(r.pg[i]) - r.exp2[i] * M_LN2) : std::log(r.pg[i]);
+        return;
+    }
     if (count > 0)
         ck(m_ctx, hmc_resolve_all(m_ctx, first, count, K, m_flags, r.pg.data() + first, r.exp2.data() + first, r.coverage.data() + first, r.nres.data() + first,
                                   r.prior.data() + (size_t) first * K, r.posterior.data() + (size_t) first * K,
@@ -969,10 +985,20 @@ void HaploBuilder::estimateFrequency(PatternSet &patterns)
     const int first = m_shard_count >= 0 ? m_shard_first : 0, count = m_shard_count >= 0 ? m_shard_count : N;
     std::vector<double> raw((size_t) 2 * Pc, 0.0), tp(Pc);
     double *f = raw.data(), *pf = raw.data() + Pc;
+    if (count < N && reduce_counts_device && count > 0) {
+        // the one exchange of an exact E-pass, on the device: the raw sums stay in HBM, are all-reduced in place and come back once
+        double *dev = nullptr;
+        ck(m_ctx, hmc_estimate_counts_device(m_ctx, first, count, m_flags, Pc, start.data(), off.data(), al.data(), m_genos->genotype_probability.data() + first,
+                                             (m_flags & HMC_FLAG_SCALED) ? pg_exp.data() + first : nullptr, &dev), "hmc_estimate_counts_device");
+        reduce_counts_device(dev, (size_t) 2 * Pc);
+        ck(m_ctx, hmc_fetch_counts(m_ctx, Pc, f, pf), "hmc_fetch_counts");
+    }
+    else {
     if (count > 0)
         ck(m_ctx, hmc_estimate_counts(m_ctx, first, count, m_flags, Pc, start.data(), off.data(), al.data(), m_genos->genotype_probability.data() + first,
                                       (m_flags & HMC_FLAG_SCALED) ? pg_exp.data() + first : nullptr, f, pf), "hmc_estimate_counts");
     if (count < N && reduce_counts) reduce_counts(raw.data(), raw.size());     // the one exchange of an exact E-pass
+    }
     hmc_normalise_counts(Pc, N, f, pf, tp.data());
     for (int i = 0; i < Pc; ++i) { patterns.pats[i].frequency = f[i]; patterns.pats[i].prefix_freq = pf[i]; patterns.pats[i].setTransitionProb(tp[i]); }
 }
@@ -1018,8 +1044,9 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
     double t0 = now_s();
     // One GPU holds every individual and the next search runs on it: the K sampled pairs stay on the device and are named by
     // their result rows (hmc_mine_patterns_resolved); only the best pair of every individual comes back.
-    const bool dev_samples = m_patterns.deviceMiningWanted() && num_patterns <= 0 && !exact_estimate && (m_shard_count < 0 || m_shard_count == N) &&
-                             !getenv("HMC_B200_HOST_SAMPLES");
+    // (sharded runs with a device-side all-gather hold every individual's rows on every rank too)
+    const bool dev_samples = m_patterns.deviceMiningWanted() && num_patterns <= 0 && !exact_estimate &&
+                             (m_shard_count < 0 || m_shard_count == N || (bool) gather_device) && !getenv("HMC_B200_HOST_SAMPLES");
     HaploBuilder::resolveAll(sample_size, r, !dev_samples);
     std::vector<int8_t> best;
     if (dev_samples) {

@@ -178,6 +178,13 @@ public:
     void setShard(int first, int count) { m_shard_first = first; m_shard_count = count; }
     std::function<void(double *, size_t)> reduce_counts;
     std::function<void(const void *, void *, size_t)> gather;
+    // The same two exchanges on DEVICE memory (preferred when set: nothing is staged through the host).  reduce_counts_device: in-place
+    // sum over ranks of n doubles at a device pointer (ncclAllReduce).  gather_device: in-place all-gather over the individuals of a
+    // device array with one row of row_bytes per panel individual -- this rank's rows [first, first+count) are valid on entry, all N on
+    // return (ncclAllGather / grouped broadcasts).  Both run after the context's stream has been synchronised.
+    std::function<void(double *, size_t)> reduce_counts_device;
+    std::function<void(void *, size_t)> gather_device;
+    bool sharded() const { return m_shard_count >= 0 && m_shard_count < (m_genos ? m_genos->N : 0); }
 
     void setGenoData(GenoData &genos);          // HaploBuilder.cpp:19-23
     void uploadPanel();                         // hmc_set_panel when the panel changed

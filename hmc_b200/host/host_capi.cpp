@@ -125,6 +125,15 @@ int hmch_set_collectives(void *p, hmch_reduce_fn reduce, hmch_gather_fn gather)
     GUARD(if (reduce) h->hm->reduce_counts = [reduce](double *b, size_t n) { reduce(b, n); }; else h->hm->reduce_counts = nullptr;
           if (gather) h->hm->gather = [gather](const void *s, void *r, size_t e) { gather(s, r, e); }; else h->hm->gather = nullptr);
 }
+typedef void (*hmch_reduce_dev_fn)(void *dev_buf, size_t n);
+typedef void (*hmch_gather_dev_fn)(void *dev_base, size_t row_bytes);
+// device-side exchanges (see HaploBuilder::reduce_counts_device / gather_device); NULL removes one
+int hmch_set_device_collectives(void *p, hmch_reduce_dev_fn reduce, hmch_gather_dev_fn gather)
+{
+    Handle *h = (Handle *) p;
+    GUARD(if (reduce) h->hm->reduce_counts_device = [reduce](double *b, size_t n) { reduce((void *) b, n); }; else h->hm->reduce_counts_device = nullptr;
+          if (gather) h->hm->gather_device = [gather](void *b, size_t e) { gather(b, e); }; else h->hm->gather_device = nullptr);
+}
 int hmch_write_reconstructed(void *p, const char *path, const char *suffix)
 {
     Handle *h = (Handle *) p;

@@ -49,6 +49,9 @@ typedef enum hmc_status {
 #define HMC_FLAG_SCALED        1u   /* exponent-only rescaling by 2^512 when max alpha < 2^-512; off = the
                                        reference's raw fp64 products, bit for bit */
 #define HMC_FLAG_KEEP_TRELLIS  2u   /* keep the last wave's trellis on the device for hmc_get_trellis (tests) */
+#define HMC_FLAG_PANEL_ROWS    4u   /* hmc_resolve_all_device only: the device result block has one row per PANEL individual (row =
+                                       individual, not individual - first); the call fills rows [first, first+count) and the rows of the
+                                       other shards are filled by an all-gather on the pointers of hmc_result_device_ptrs (multi-GPU) */
 
 #define HMC_MAX_ALLELES 16          /* alleles per locus (Amax) supported by the packed genotype / pair encoding */
 #define HMC_MAX_K       32          /* sample_size */
@@ -112,6 +115,17 @@ int hmc_resolve_all(hmc_ctx *ctx, int first, int count, int K, unsigned flags, d
 int hmc_resolve_all_device(hmc_ctx *ctx, int first, int count, int K, unsigned flags);
 int hmc_fetch_results(hmc_ctx *ctx, double *out_pg, int32_t *out_exp, double *out_cov, int32_t *out_nres, double *out_prior,
                       double *out_post, int8_t *out_haps, double *out_ll);
+
+/* Multi-GPU exchange without host staging (one process per GPU): device pointers of the result block of the last
+ * hmc_resolve_all_device call -- ptrs[7] = {pg, exp, coverage, nres, prior, posterior, haps}, row_bytes[7] = bytes per individual --
+ * for an in-place all-gather over the individuals (ncclAllGather / torch.distributed on the same device).  With HMC_FLAG_PANEL_ROWS the
+ * block has N rows; after the exchange hmc_fetch_results / hmc_fetch_best_haps / hmc_mine_patterns_resolved / hmc_compare see all of
+ * them (this replaces the gather that HaploModel::resolveAll does by being one loop, HaploModel.cpp:86-109). */
+int hmc_result_device_ptrs(hmc_ctx *ctx, void *ptrs[7], int64_t row_bytes[7]);
+/* Raw count vector of the last hmc_estimate_counts_device call (after the caller's in-place all-reduce): out_freq / out_prefix [Pc]. */
+int hmc_fetch_counts(hmc_ctx *ctx, int Pc, double *out_freq, double *out_prefix);
+/* The CUDA stream the context's kernels run on (cudaStream_t), so that a collective can be ordered after them. */
+void *hmc_stream(hmc_ctx *ctx);
 
 /* HaploBuilder::estimateFrequency(vector<HaploPattern*>&) (HaploBuilder.cpp:274-332): expected
  * pattern counts over individuals [first, first+count) for an explicit candidate list (which may
