@@ -84,6 +84,8 @@ struct hmc_ctx {
     DevBuf<signed char> d_raw;      // staging of the unpacked genotypes (kept: cudaMalloc/cudaFree per call cost 100s of ms)
     DevBuf<int> d_order;
     std::vector<int> h_order, h_rank;
+    DevBuf<long long> d_work;       // forward-kernel cycles per individual of the last pass that resolved it (0 = not yet): the next pass's work order
+    std::vector<long long> h_work;
     std::vector<int> h_nall;
 
     // model
@@ -370,10 +372,14 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     CK(ctx->d_final_exp.ensure(wave_cap));
     if (flags & HMC_FLAG_SCALED) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * (L + 1)));
 
-    // pending individuals, heaviest first
+    // pending individuals, heaviest first: by the time the previous pass over the same panel spent on them (EM iterations and
+    // the E-passes of an M-step resolve the same individuals again and again), else by missing genotypes
     std::vector<int> pending;
     pending.reserve(count);
     for (int q = 0; q < ctx->N; ++q) { const int ind = ctx->h_order[q]; if (ind >= first && ind < first + count) pending.push_back(ind); }
+    CK(ctx->d_work.ensure(ctx->N));
+    if ((int) ctx->h_work.size() != ctx->N) { ctx->h_work.assign(ctx->N, 0); CK(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(long long) * ctx->N, ctx->stream)); }
+    else std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return ctx->h_work[a] > ctx->h_work[b]; });
     std::vector<int> big;
     std::vector<int> h_status;
     bool big_mode = false;
@@ -405,6 +411,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         fp.status = ctx->d_status.p; fp.final_exp = ctx->d_final_exp.p;
         fp.locus_exp = fp.scaled ? ctx->d_locus_exp.p : nullptr;
         fp.queue = ctx->d_flags.p + 1; fp.counters = ctx->d_counters.p;
+        fp.work = ctx->d_work.p;
         fp.ind_cycles = nullptr;
         if (getenv("HMC_B200_DEBUG_CYCLES")) { CK(ctx->d_cycles.ensure((size_t) wave_cap * 8)); CK(cudaMemsetAsync(ctx->d_cycles.p, 0, sizeof(long long) * 8 * n_wave, ctx->stream)); fp.ind_cycles = ctx->d_cycles.p; }
 
@@ -466,6 +473,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     }
     long long hc[32];
     CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctx->h_work.data(), ctx->d_work.p, sizeof(long long) * ctx->N, cudaMemcpyDeviceToHost));
     if (getenv("HMC_B200_PRINT_PASSES"))
         for (int b = 8; b < 24; b += 8)
             fprintf(stderr, "%s pass Mcycles: [0] %lld  [1] %lld  [2] %lld  [3] %lld  [4] %lld  [5] %lld  [7] %lld | [6] %lld\n", b == 8 ? "fast " : "spill",
@@ -514,7 +522,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_succ16.release();
+    ctx->d_packed.release(); ctx->d_raw.release(); ctx->d_linfo.release(); ctx->d_order.release(); ctx->d_work.release(); ctx->d_succ16.release();
     ctx->d_succ.release(); ctx->d_start.release(); ctx->d_heads.release(); ctx->d_head_lut.release(); ctx->d_tp.release(); ctx->d_freq.release();
     ctx->d_last.release(); ctx->d_al_off.release(); ctx->d_al.release(); ctx->d_end_tmp.release(); ctx->d_model_err.release(); ctx->d_miss.release(); ctx->d_counts_snap.release();
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
@@ -542,6 +550,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     ctx->ecache.valid = false;
     ctx->have_model = false;        // the automaton tables (successor stride, head table) belong to the previous panel's allele tables
     ctx->r_count = 0;
+    ctx->h_work.clear();
     ctx->N = N; ctx->L = L; ctx->Amax = Amax;
     ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
     const int per = 32 / (2 * ctx->bits);
@@ -596,6 +605,7 @@ int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const u
     ctx->ecache.valid = false;
     ctx->have_model = false;
     ctx->r_count = 0;
+    ctx->h_work.clear();
     ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
     const int per = 32 / (2 * bits);
     ctx->words = (L + per - 1) / per;

@@ -100,6 +100,7 @@ struct FwdParams {
     int *locus_exp;             // [n_wave][L+1] cumulative exponent (scaled mode) or null
     int *queue;                 // work-queue head
     long long *counters;        // steps, states, max_states, arrivals, -, spill steps
+    long long *work;            // [N] SM cycles the forward kernel spent on every individual it resolved (orders the next pass: longest first)
     long long *ind_cycles;      // [n_wave][8] per-individual diagnostics (cycles, states, ...) or null
 };
 

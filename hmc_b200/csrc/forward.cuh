@@ -698,6 +698,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 unsigned long long t_end_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns)); d[6] = (long long) t_end_ns; d[7] = blockIdx.x;
             }
             if (status == ST_DONE) {
+                if (p.work) p.work[ind] = clock64() - t_begin;      // (SM cycles: a better predictor of the next pass's time than the state count)
                 atomicAdd((unsigned long long *) p.counters + 0, (unsigned long long) c_steps);
                 atomicAdd((unsigned long long *) p.counters + 1, (unsigned long long) c_states);
                 atomicMax((long long *) p.counters + 2, c_max);

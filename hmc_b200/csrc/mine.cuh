@@ -61,7 +61,7 @@ __global__ void mine_roots_kernel(MineParams m, long long *need, long long *pack
     m.nd.flags[s] = ext ? MINE_EXTENDED : 0;
     need[s] = 0;
     const int nchild = ext ? __popc(m.linfo[s] >> 8) : 0;
-    packed[s] = ((long long) (ext ? 1 : 0) << 40) | nchild;
+    packed[s] = ((long long) (ext ? 1 : 0) << 32) | nchild;
 }
 
 template <bool SAMPLES, bool FILL>
@@ -178,7 +178,7 @@ __global__ void mine_decide_kernel(MineParams m, int c0, int n, long long *need,
     m.nd.flags[c] = (unsigned char) ((rel ? MINE_RELEASED : 0) | (ext ? MINE_EXTENDED : 0));
     need[t] = ext ? m.nd.cnt[c] : 0;
     const int nchild = ext ? __popc(m.linfo[start + len] >> 8) : 0;
-    packed[t] = ((long long) (ext ? 1 : 0) << 40) | nchild;
+    packed[t] = ((long long) (ext ? 1 : 0) << 32) | nchild;
 }
 
 struct MineTotals { long long list_total, n_ext, n_child; };
@@ -193,15 +193,15 @@ __global__ void mine_link_kernel(MineParams m, int c0, int n, const long long *n
     m.nd.loff[c] = need_scan[t];
     const long long ps = packed_scan[t];
     if (m.nd.flags[c] & MINE_EXTENDED) {
-        ext_next[(int) (ps >> 40)] = c;
-        m.nd.cbase[c] = child_begin_next + (int) (ps & 0xFFFFFFFFFFll);
+        ext_next[(int) (ps >> 32)] = c;
+        m.nd.cbase[c] = child_begin_next + (int) (ps & 0xFFFFFFFFll);
     }
     else m.nd.cbase[c] = -1;
     if (t == n - 1) {
         const long long pt = ps + packed[t];
         tot->list_total = need_scan[t] + need[t];
-        tot->n_ext = pt >> 40;
-        tot->n_child = pt & 0xFFFFFFFFFFll;
+        tot->n_ext = pt >> 32;
+        tot->n_child = pt & 0xFFFFFFFFll;
     }
 }
 

@@ -109,17 +109,23 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
             CK(grow(mp.rows, (size_t) n_items));
             CK(cudaMemcpyAsync(mp.rows.p, sample_rows, sizeof(int) * n_items, cudaMemcpyHostToDevice, st));
             mine_transpose_rows_kernel<<<tg, tb, 0, st>>>(ctx->d_haps.p, mp.rows.p, n_items, L, mp.a0.p);
+            CK(cudaGetLastError());
+            CK(cudaGetLastError());
         }
         else {
             CK(grow(mp.samples_raw, (size_t) n_items * L));
             CK(cudaMemcpyAsync(mp.samples_raw.p, sample_haps, (size_t) n_items * L, cudaMemcpyHostToDevice, st));
             mine_transpose_kernel<<<tg, tb, 0, st>>>(mp.samples_raw.p, n_items, L, 1, mp.a0.p, nullptr);
+            CK(cudaGetLastError());
+            CK(cudaGetLastError());
         }
         mp.panel_serial = -1;
     }
     else if (mp.panel_serial != ctx->panel_serial) {
         CK(mp.a0.ensure((size_t) N * L)); CK(mp.a1.ensure((size_t) N * L));
         mine_transpose_kernel<<<tg, tb, 0, st>>>(ctx->d_raw.p, N, L, 2, mp.a0.p, mp.a1.p);
+        CK(cudaGetLastError());
+        CK(cudaGetLastError());
         mp.panel_serial = ctx->panel_serial;
     }
     CK(mp.min_len.ensure(L)); CK(mp.max_len.ensure(L)); CK(mp.tot.ensure(1)); CK(mp.o_P.ensure(1));
@@ -155,11 +161,13 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         const unsigned gb = (unsigned) ((n + 255) / 256);
         if (d == 0) mine_roots_kernel<<<gb, 256, 0, st>>>(m, mp.need.p, mp.packed.p);
         else mine_decide_kernel<<<gb, 256, 0, st>>>(m, (int) c0, (int) n, mp.need.p, mp.packed.p);
+        if (cudaError_t e_ = cudaGetLastError()) return ctx->fail(HMC_ERR_CUDA, "mine_roots / mine_decide launch (level %d, grid %u, n %lld): %s", d, gb, n, cudaGetErrorString(e_));
         int rc = mine_scan(ctx, mp, mp.need.p, mp.need_scan.p, n);
         if (rc) return rc;
         rc = mine_scan(ctx, mp, mp.packed.p, mp.packed_scan.p, n);
         if (rc) return rc;
         mine_link_kernel<<<gb, 256, 0, st>>>(m, (int) c0, (int) n, mp.need.p, mp.need_scan.p, mp.packed.p, mp.packed_scan.p, mp.ext[epar ^ 1].p, (int) node_end, mp.tot.p);
+        CK(cudaGetLastError());
         MineTotals t;
         CK(cudaMemcpyAsync(&t, mp.tot.p, sizeof t, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -175,11 +183,13 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
             const unsigned gw = (unsigned) std::min<long long>(((long long) n_par * 32 + 255) / 256, (long long) ctx->sms * 32);
             if (samples) mine_sweep_kernel<true, true><<<gw, 256, 0, st>>>(m, n_par, par);
             else mine_sweep_kernel<false, true><<<gw, 256, 0, st>>>(m, n_par, par);
+            if (cudaError_t e_ = cudaGetLastError()) return ctx->fail(HMC_ERR_CUDA, "mine_sweep<FILL> launch (grid %u, %d parents): %s", gw, n_par, cudaGetErrorString(e_));
             mp.swept += prev_in; mp.written += t.list_total;
         }
         if (d > 0) par ^= 1;
         epar ^= 1;
         if (t.n_ext == 0 || t.n_child == 0) break;
+        if (t.n_ext > 0x7FFFFFF0ll / std::max(1, ctx->Amax)) return ctx->fail(HMC_ERR_LIMIT, "pattern trie exceeds 2^31 nodes");     // (keeps the packed child count below 2^32)
         if (node_end + t.n_child > 0x7FFFFFF0ll) return ctx->fail(HMC_ERR_LIMIT, "pattern trie exceeds 2^31 nodes");
         CK(mp.reserve_nodes((size_t) (node_end + t.n_child), (size_t) node_end));
         refresh();
@@ -187,6 +197,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         const unsigned gw = (unsigned) std::min<long long>((t.n_ext * 32 + 255) / 256, (long long) ctx->sms * 32);
         if (samples) mine_sweep_kernel<true, false><<<gw, 256, 0, st>>>(m, (int) t.n_ext, par);
         else mine_sweep_kernel<false, false><<<gw, 256, 0, st>>>(m, (int) t.n_ext, par);
+        if (cudaError_t e_ = cudaGetLastError()) return ctx->fail(HMC_ERR_CUDA, "mine_sweep<COUNT> launch (grid %u, %lld parents): %s", gw, (long long) t.n_ext, cudaGetErrorString(e_));
         prev_ext = (int) t.n_ext;
         prev_in = d == 0 ? t.n_ext * (long long) n_items : t.list_total;
         mp.swept += prev_in;
@@ -201,6 +212,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         if (cnt > 0) mine_sub_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(m, (int) b, (int) cnt);
     }
     mine_root_ids_kernel<<<1, 32, 0, st>>>(m, mp.o_P.p);
+    CK(cudaGetLastError());
     for (int d = 0; d + 1 < (int) level_begin.size(); ++d) {
         const long long b = level_begin[d], cnt = level_begin[d + 1] - b;
         if (cnt > 0) mine_ids_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(m, (int) b, (int) cnt);
@@ -226,8 +238,10 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         CK(grow(mp.o_al, (size_t) mp.n_alleles));
         o.al = mp.o_al.p;
         mine_alleles_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(m, o, P);
+        CK(cudaGetLastError());
         CK(grow(mp.o_rec, (size_t) P));
         mine_records_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(o, mp.o_rec.p, P);
+        CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
