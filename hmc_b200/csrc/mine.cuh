@@ -30,6 +30,7 @@ struct MineNodes {                  // SoA over all trie nodes of all start loci
 
 struct MineParams {
     int n_items, L, Amax;           // n_items: individuals (genotype branch) or sampled haplotypes
+    int s0, nroots;                 // the start loci [s0, s0 + nroots) of this batch: trie node r < nroots is the root of start s0 + r
     const signed char *a0, *a1;     // locus-major allele indices [L][n_items]; a1 only in the genotype branch
     const double *w;                // sample weights
     const double *af;               // [L][Amax]
@@ -54,13 +55,14 @@ __device__ __forceinline__ void mine_rule(const MineParams &m, int start, int le
 __global__ void mine_roots_kernel(MineParams m, long long *need, long long *packed)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m.L) return;
+    if (s >= m.nroots) return;
+    const int st = m.s0 + s;
     bool rel, ext;
-    mine_rule(m, s, 0, 1.0, rel, ext);
-    m.nd.parent[s] = -1; m.nd.start[s] = s; m.nd.len[s] = 0; m.nd.al[s] = -1; m.nd.freq[s] = 1.0; m.nd.cnt[s] = 0;
+    mine_rule(m, st, 0, 1.0, rel, ext);
+    m.nd.parent[s] = -1; m.nd.start[s] = st; m.nd.len[s] = 0; m.nd.al[s] = -1; m.nd.freq[s] = 1.0; m.nd.cnt[s] = 0;
     m.nd.flags[s] = ext ? MINE_EXTENDED : 0;
     need[s] = 0;
-    const int nchild = ext ? __popc(m.linfo[s] >> 8) : 0;
+    const int nchild = ext ? __popc(m.linfo[st] >> 8) : 0;
     packed[s] = ((long long) (ext ? 1 : 0) << 32) | nchild;
 }
 
@@ -225,7 +227,7 @@ __global__ void mine_root_ids_kernel(MineParams m, long long *P_out)
 {
     if (blockIdx.x || threadIdx.x) return;
     long long run = 0;
-    for (int s = m.L - 1; s >= 0; --s) { m.nd.idb[s] = (int) run; run += m.nd.sub[s]; }
+    for (int s = m.nroots - 1; s >= 0; --s) { m.nd.idb[s] = (int) run; run += m.nd.sub[s]; }
     *P_out = run;
 }
 
@@ -272,6 +274,12 @@ __global__ void mine_alleles_kernel(MineParams m, MineOut o, long long P)
     signed char *dst = o.al + o.al_off[id];
     for (int k = (int) m.nd.len[c] - 1; k >= 0; --k) { dst[k] = m.nd.al[c]; c = m.nd.parent[c]; }
     if (id == P - 1) o.al_off[P] = o.al_off[id] + o.len64[id];
+}
+
+__global__ void mine_add_offset_kernel(long long *v, long long n, long long add)
+{
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i < n) v[i] += add;
 }
 
 // the pattern list as the host's records (include/hmc_b200.h hmc_pattern_rec)

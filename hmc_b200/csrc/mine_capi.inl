@@ -131,11 +131,15 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     CK(mp.min_len.ensure(L)); CK(mp.max_len.ensure(L)); CK(mp.tot.ensure(1)); CK(mp.o_P.ensure(1));
     CK(cudaMemcpyAsync(mp.min_len.p, min_len, sizeof(int) * L, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(mp.max_len.p, max_len, sizeof(int) * L, cudaMemcpyHostToDevice, st));
-    CK(mp.reserve_nodes(std::max<size_t>((size_t) L, (size_t) 1 << 23), 0));
-    {   // first guess for the match lists: every item once per start locus (exact for fully resolved samples)
-        const size_t guess = std::min<size_t>((size_t) n_items * L * (samples ? 1 : 4) + 1024, (size_t) 1 << 30);
-        for (int i = 0; i < 2; ++i) { CK(grow(mp.list_id[i], guess)); if (!samples) CK(grow(mp.list_fr[i], guess)); }
-    }
+    // The tries of different start loci are independent, and a level's match lists hold every (item, start) pair as often as the item
+    // matches a candidate of that start (~100x at the deep levels of a long panel): the start loci are mined in batches of bounded
+    // (item, start) pairs so that the lists of a level fit the device whatever the panel's size.  Batches go from the highest start
+    // down -- the reference releases its candidate stack from the back (PatternManager.cpp:106-142), so their patterns are consecutive
+    // id ranges and the batch results are appended.
+    long long pair_budget = 20000000;
+    if (const char *env = getenv("HMC_B200_MINE_PAIRS")) pair_budget = std::max(1ll, atoll(env));
+    const int batch = (int) std::max<long long>(1, std::min<long long>(L, pair_budget / std::max(1, n_items)));
+    CK(mp.reserve_nodes(std::max<size_t>((size_t) std::min(L, batch), (size_t) 1 << 23), 0));
 
     MineParams m = {};
     auto refresh = [&]() {
@@ -146,11 +150,32 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         m.nd = mp.nd;
         for (int i = 0; i < 2; ++i) { m.list_id[i] = mp.list_id[i].p; m.list_fr[i] = mp.list_fr[i].p; }
     };
+    // output arrays grow batch by batch, keeping what earlier batches appended
+    auto keep = [&](auto &buf, size_t live, size_t want) -> cudaError_t {
+        if (want <= buf.n) return cudaSuccess;
+        typedef typename std::remove_reference<decltype(*buf.p)>::type T;
+        const size_t cap = std::max<size_t>(want + want / 4, (size_t) 1 << 20);
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **) &q, cap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (buf.p && live) e = cudaMemcpyAsync(q, buf.p, live * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (buf.p) cudaFree(buf.p);
+        buf.p = q; buf.n = cap;
+        return e;
+    };
+    mp.max_list = 0; mp.swept = 0; mp.written = 0; mp.nodes = 0; mp.levels = 0;
+    long long P_total = 0, al_total = 0;
+    for (int s1 = L; s1 > 0; s1 -= batch) {
+    const int s0 = std::max(0, s1 - batch), nroots = s1 - s0;
+    {   // first guess for the match lists: every item once per start locus (exact for fully resolved samples)
+        const size_t guess = std::min<size_t>((size_t) n_items * nroots * (samples ? 1 : 4) + 1024, (size_t) 1 << 30);
+        for (int i = 0; i < 2; ++i) { CK(grow(mp.list_id[i], guess)); if (!samples) CK(grow(mp.list_fr[i], guess)); }
+    }
     std::vector<long long> level_begin;
     long long node_end = 0;
     int par = 0, epar = 0, prev_ext = 0;
-    long long c0 = 0, n = L;            // the level whose nodes were just created (level 0: the roots)
-    mp.max_list = 0; mp.swept = 0; mp.written = 0;
+    long long c0 = 0, n = nroots;       // the level whose nodes were just created (level 0: the roots)
     long long prev_in = 0;              // entries in the lists of the current parents
     for (int d = 0;; ++d) {
         level_begin.push_back(c0);
@@ -158,6 +183,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         CK(grow(mp.need, n)); CK(grow(mp.need_scan, n)); CK(grow(mp.packed, n)); CK(grow(mp.packed_scan, n));
         CK(grow(mp.ext[epar ^ 1], n));
         refresh();
+        m.s0 = s0; m.nroots = nroots;
         const unsigned gb = (unsigned) ((n + 255) / 256);
         if (d == 0) mine_roots_kernel<<<gb, 256, 0, st>>>(m, mp.need.p, mp.packed.p);
         else mine_decide_kernel<<<gb, 256, 0, st>>>(m, (int) c0, (int) n, mp.need.p, mp.packed.p);
@@ -178,6 +204,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
             CK(grow(mp.list_id[par ^ 1], (size_t) t.list_total));
             if (!samples) CK(grow(mp.list_fr[par ^ 1], (size_t) t.list_total));
             refresh();
+            m.s0 = s0; m.nroots = nroots;
             m.ext = mp.ext[epar].p;
             const int n_par = prev_ext;
             const unsigned gw = (unsigned) std::min<long long>(((long long) n_par * 32 + 255) / 256, (long long) ctx->sms * 32);
@@ -193,6 +220,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         if (node_end + t.n_child > 0x7FFFFFF0ll) return ctx->fail(HMC_ERR_LIMIT, "pattern trie exceeds 2^31 nodes");
         CK(mp.reserve_nodes((size_t) (node_end + t.n_child), (size_t) node_end));
         refresh();
+        m.s0 = s0; m.nroots = nroots;
         m.ext = mp.ext[epar].p;
         const unsigned gw = (unsigned) std::min<long long>((t.n_ext * 32 + 255) / 256, (long long) ctx->sms * 32);
         if (samples) mine_sweep_kernel<true, false><<<gw, 256, 0, st>>>(m, (int) t.n_ext, par);
@@ -204,13 +232,15 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
         c0 = node_end; n = t.n_child;
     }
     level_begin.push_back(node_end);
-    mp.nodes = node_end; mp.levels = (long long) level_begin.size() - 1;
+    mp.nodes += node_end; mp.levels = std::max<long long>(mp.levels, (long long) level_begin.size() - 1);
     // ids: subtree sizes bottom-up, bases top-down
     refresh();
+    m.s0 = s0; m.nroots = nroots;
     for (int d = (int) level_begin.size() - 2; d >= 0; --d) {
         const long long b = level_begin[d], cnt = level_begin[d + 1] - b;
         if (cnt > 0) mine_sub_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(m, (int) b, (int) cnt);
     }
+    CK(mp.o_P.ensure(1));
     mine_root_ids_kernel<<<1, 32, 0, st>>>(m, mp.o_P.p);
     CK(cudaGetLastError());
     for (int d = 0; d + 1 < (int) level_begin.size(); ++d) {
@@ -221,26 +251,35 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     CK(cudaMemcpyAsync(&P, mp.o_P.p, sizeof P, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    mp.P = P; mp.n_alleles = 0; mp.pin_valid = false; mp.handed_over = false;
-    if (P > 0) {
-        CK(grow(mp.o_start, P)); CK(grow(mp.o_end, P)); CK(grow(mp.o_node, P)); CK(grow(mp.o_freq, P)); CK(grow(mp.o_prefix, P)); CK(grow(mp.o_tp, P));
-        CK(grow(mp.o_len, P)); CK(grow(mp.o_aloff, P + 1));
-        MineOut o = {mp.o_start.p, mp.o_end.p, mp.o_freq.p, mp.o_prefix.p, mp.o_tp.p, mp.o_len.p, mp.o_aloff.p, nullptr, mp.o_node.p};
-        const long long cnt = node_end - L;
-        if (cnt > 0) mine_emit_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(m, o, L, (int) cnt);
-        int rc = mine_scan(ctx, mp, mp.o_len.p, mp.o_aloff.p, P);
+    if (P_total + P > 0x7FFFFFF0ll) return ctx->fail(HMC_ERR_LIMIT, "more than 2^31 patterns");
+    if (P > 0) {        // this batch's patterns are ids [P_total, P_total + P)
+        const size_t Pt = (size_t) P_total, Pn = (size_t) (P_total + P);
+        CK(keep(mp.o_start, Pt, Pn)); CK(keep(mp.o_end, Pt, Pn)); CK(keep(mp.o_freq, Pt, Pn)); CK(keep(mp.o_prefix, Pt, Pn)); CK(keep(mp.o_tp, Pt, Pn));
+        CK(keep(mp.o_aloff, Pt + 1, Pn + 1));
+        CK(grow(mp.o_node, P)); CK(grow(mp.o_len, P));
+        MineOut o = {mp.o_start.p + Pt, mp.o_end.p + Pt, mp.o_freq.p + Pt, mp.o_prefix.p + Pt, mp.o_tp.p + Pt, mp.o_len.p, mp.o_aloff.p + Pt, nullptr, mp.o_node.p};
+        const long long cnt = node_end - nroots;
+        if (cnt > 0) mine_emit_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(m, o, nroots, (int) cnt);
+        int rc = mine_scan(ctx, mp, mp.o_len.p, mp.o_aloff.p + Pt, P);
         if (rc) return rc;
+        if (al_total) mine_add_offset_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(mp.o_aloff.p + Pt, P, al_total);
         long long last_off = 0, last_len = 0;
-        CK(cudaMemcpyAsync(&last_off, mp.o_aloff.p + (P - 1), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&last_off, mp.o_aloff.p + Pt + (P - 1), 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&last_len, mp.o_len.p + (P - 1), 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        mp.n_alleles = last_off + last_len;
-        CK(grow(mp.o_al, (size_t) mp.n_alleles));
+        const long long al_new = last_off + last_len;
+        CK(keep(mp.o_al, (size_t) al_total, (size_t) al_new + 1));
         o.al = mp.o_al.p;
         mine_alleles_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(m, o, P);
         CK(cudaGetLastError());
-        CK(grow(mp.o_rec, (size_t) P));
-        mine_records_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, st>>>(o, mp.o_rec.p, P);
+        P_total += P; al_total = al_new;
+    }
+    }   // batches of start loci
+    mp.P = P_total; mp.n_alleles = al_total; mp.pin_valid = false; mp.handed_over = false;
+    if (P_total > 0) {
+        MineOut o = {mp.o_start.p, mp.o_end.p, mp.o_freq.p, mp.o_prefix.p, mp.o_tp.p, nullptr, mp.o_aloff.p, mp.o_al.p, nullptr};
+        CK(grow(mp.o_rec, (size_t) P_total));
+        mine_records_kernel<<<(unsigned) ((P_total + 255) / 256), 256, 0, st>>>(o, mp.o_rec.p, P_total);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], st));

@@ -16,8 +16,16 @@ pytestmark = pytest.mark.gpu
 KEYS = ("start", "end", "freq", "prefix", "tp", "succ", "heads", "al")
 
 
+@pytest.fixture(params=[None, "96"], ids=["one-batch", "start-batches"])
+def mine_batches(request, monkeypatch):
+    """The start loci are mined in batches of bounded (item, start) pairs; "96" forces batches of 1-3 start loci on the small panels."""
+    if request.param:
+        monkeypatch.setenv("HMC_B200_MINE_PAIRS", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", [n for n in CASES if n != "g7_bynum"])
-def test_first_model_matches_reference_dump(name):
+def test_first_model_matches_reference_dump(name, mine_batches):
     """Genotype branch (checkFrequencyWithExtension :205-251 / getMatchingFrequency) on every golden panel."""
     d = golden(name)
     hm = HaploModel(**{**model_opts(name), "device_mining": 1})
@@ -61,7 +69,7 @@ def _models(g, kind="S", **opts):
 ])
 @pytest.mark.parametrize("opts", [dict(), dict(max_pattern_len=4), dict(min_pattern_len=2, max_pattern_len=12), dict(min_freq=0.05, min_freq_abs=-1.0),
                                   dict(model="MC", mc_order=2)])
-def test_device_equals_host_miner(cfg, opts):
+def test_device_equals_host_miner(cfg, opts, mine_batches):
     c = dict(cfg)
     kind = "M" if c.get("alleles", 2) > 2 else "S"
     if c["n_loci"] < opts.get("min_pattern_len", 1):
@@ -74,7 +82,7 @@ def test_device_equals_host_miner(cfg, opts):
 
 
 @pytest.mark.parametrize("name", ["g4_em", "g2_missing"])
-def test_sampling_em_identical_with_device_mining(name):
+def test_sampling_em_identical_with_device_mining(name, mine_batches):
     """Sampling branch (:180-191,252-263): every EM iteration re-mines on the K sampled haplotypes; the whole trace,
     the pattern counts and the final phasing must not depend on where the search ran."""
     out = []
