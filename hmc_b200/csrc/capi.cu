@@ -86,6 +86,7 @@ struct hmc_ctx {
     std::vector<int> h_order, h_rank;
     DevBuf<long long> d_work;       // forward-kernel cycles per individual of the last pass that resolved it (0 = not yet): the next pass's work order
     std::vector<long long> h_work;
+    double est_units[2] = {0, 0};   // arena units (8 B) one individual's trellis took in the last waves, resolve / E-step mode: sizes the next wave
     std::vector<int> h_nall;
 
     // model
@@ -388,7 +389,14 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
 
     while (!pending.empty() || (!big_mode && !big.empty())) {
         if (pending.empty()) { big_mode = true; pending.swap(big); }
-        const int n_wave = (int) std::min<size_t>(pending.size(), (size_t) wave_cap);
+        // The arena is a bump allocator: everything a wave starts must fit, and what is still running when it fills up is lost work.  So a
+        // wave takes only as many individuals as the footprint seen so far says will fit (the first wave of a panel starts blind).
+        int n_wave = (int) std::min<size_t>(pending.size(), (size_t) wave_cap);
+        {
+            const double cap_units = (double) ctx->d_arena.n * (estep ? 1.0 : fwd_share);
+            const double est = ctx->est_units[estep ? 1 : 0];
+            if (est > 0 && !big_mode) n_wave = (int) std::max<double>(1.0, std::min<double>((double) n_wave, 0.97 * cap_units / est));
+        }
         ScratchPool &pl = big_mode ? ctx->big_pool : ctx->pool;
         int slots;
         if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, 1 << 20, 1 << 22, 1 << 23); }
@@ -464,9 +472,28 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             }
         }
         ++waves;
+        {   // footprint estimate for the next wave: arena used / individuals that consumed it (the ones cut off were close to done: the
+            // CTAs of a wave advance together), with a margin; heaviest individuals come first, so this leans high
+            unsigned long long cur = 0;
+            CK(cudaMemcpy(&cur, ctx->d_cursor.p, sizeof cur, cudaMemcpyDeviceToHost));
+            const int consumers = done + kb_fail + std::min<int>((int) again.size() - kb_fail, slots);
+            if (consumers > 0 && cur > 0 && !big_mode) {
+                const double est = 1.2 * (double) cur / consumers;
+                double &e = ctx->est_units[estep ? 1 : 0];
+                e = (done + kb_fail == n_wave) ? std::max(est, 0.5 * e) : std::max(est, e);      // everything fitted: follow the estimate down slowly
+            }
+        }
+        if (getenv("HMC_B200_PRINT_WAVES")) {
+            int hist[8] = {0};
+            for (int q = 0; q < n_wave; ++q) ++hist[h_status[q] & 7];
+            unsigned long long cur = 0;
+            cudaMemcpy(&cur, ctx->d_cursor.p, sizeof cur, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "wave %d: %d individuals -> pending %d done %d nomem %d too_big %d no_head %d nomem_kbest %d; arena cursor %.1f of %.1f GB (forward share %.2f)\n", waves, n_wave,
+                    hist[ST_PENDING], hist[ST_DONE], hist[ST_NOMEM], hist[ST_TOO_BIG], hist[ST_NO_HEAD], hist[ST_NOMEM_KBEST], cur * 8 / 1e9, ctx->d_arena.n * 8 / 1e9, fwd_share);
+        }
         // every individual of the wave ran out of arena: the first one had it to itself (the queue hands them out in order), so it can never fit
         if (kb_fail) fwd_share *= 0.5;      // the K-best kernel ran out of room behind the trellis: leave it more in the next wave
-        if (done == 0 && !again.empty() && (int) again.size() == n_wave && (kb_fail == 0 || fwd_share < 0.01))
+        if (done == 0 && !again.empty() && (int) again.size() == n_wave && n_wave == 1 && (kb_fail == 0 || fwd_share < 0.01))
             return ctx->fail(HMC_ERR_NOMEM, "trellis arena (%zu MB) cannot hold a single individual", ctx->d_arena.n * 8 >> 20);
         pending.erase(pending.begin(), pending.begin() + n_wave);
         pending.insert(pending.begin(), again.begin(), again.end());
@@ -551,6 +578,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     ctx->have_model = false;        // the automaton tables (successor stride, head table) belong to the previous panel's allele tables
     ctx->r_count = 0;
     ctx->h_work.clear();
+    ctx->est_units[0] = ctx->est_units[1] = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax;
     ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
     const int per = 32 / (2 * ctx->bits);
@@ -606,6 +634,7 @@ int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const u
     ctx->have_model = false;
     ctx->r_count = 0;
     ctx->h_work.clear();
+    ctx->est_units[0] = ctx->est_units[1] = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
     const int per = 32 / (2 * bits);
     ctx->words = (L + per - 1) / per;

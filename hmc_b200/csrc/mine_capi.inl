@@ -137,6 +137,10 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     // down -- the reference releases its candidate stack from the back (PatternManager.cpp:106-142), so their patterns are consecutive
     // id ranges and the batch results are appended.
     long long pair_budget = 20000000;
+    {   // the lists of a deep level hold ~100 entries of 12 bytes per pair, twice (ping-pong): keep them within a quarter of what is free
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) pair_budget = std::min<long long>(pair_budget, std::max<long long>(1000000, (long long) (fr / 4 / 2400)));
+    }
     if (const char *env = getenv("HMC_B200_MINE_PAIRS")) pair_budget = std::max(1ll, atoll(env));
     const int batch = (int) std::max<long long>(1, std::min<long long>(L, pair_budget / std::max(1, n_items)));
     CK(mp.reserve_nodes(std::max<size_t>((size_t) std::min(L, batch), (size_t) 1 << 23), 0));
@@ -154,7 +158,7 @@ static int run_mine(hmc_ctx *ctx, MinePool &mp, int n_samples, const int8_t *sam
     auto keep = [&](auto &buf, size_t live, size_t want) -> cudaError_t {
         if (want <= buf.n) return cudaSuccess;
         typedef typename std::remove_reference<decltype(*buf.p)>::type T;
-        const size_t cap = std::max<size_t>(want + want / 4, (size_t) 1 << 20);
+        const size_t cap = want * sizeof(T) > ((size_t) 1 << 30) ? want : std::max<size_t>(want + want / 4, (size_t) 1 << 20);       // (no headroom once it is large)
         T *q = nullptr;
         cudaError_t e = cudaMalloc((void **) &q, cap * sizeof(T));
         if (e != cudaSuccess) return e;
