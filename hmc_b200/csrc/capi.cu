@@ -258,26 +258,26 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
 #ifdef FWD_SWEEP
     if (const char *env = getenv("HMC_B200_FWD_CFG")) {     // kernel-configuration experiments
         switch (atoi(env)) {
-            case 0: return launch_forward_t<128, 256, 6>(p, grid, st, occ);
-            case 1: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
-            case 2: return launch_forward_t<256, 512, 2>(p, grid, st, occ);
-            case 3: return launch_forward_t<256, 1024, 2>(p, grid, st, occ);
-            case 4: return launch_forward_t<512, 512, 2>(p, grid, st, occ);
-            case 5: return launch_forward_t<512, 1024, 1>(p, grid, st, occ);
-            case 6: return launch_forward_t<512, 1024, 2>(p, grid, st, occ);
-            case 7: return launch_forward_t<1024, 2048, 1>(p, grid, st, occ);
-            case 8: return launch_forward_t<256, 512, 4>(p, grid, st, occ);
+            case 0: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
+            case 1: return launch_forward_t<128, 256, 6>(p, grid, st, occ);
+            case 2: return launch_forward_t<128, 128, 8>(p, grid, st, occ);
+            case 3: return launch_forward_t<128, 128, 10>(p, grid, st, occ);
+            case 4: return launch_forward_t<256, 128, 5>(p, grid, st, occ);
+            case 5: return launch_forward_t<64, 128, 16>(p, grid, st, occ);
+            case 6: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
+            case 7: return launch_forward_t<512, 512, 2>(p, grid, st, occ);
+            case 8: return launch_forward_t<64, 64, 20>(p, grid, st, occ);
             default: break;
         }
     }
 #endif
-    // measured on C2 (profiles/README.md, round 2): 256 threads per individual with 4 resident CTAs per SM is the best of the swept
-    // configurations; beyond ~16-24 resident warps per SM more CTAs only add L2 / DRAM traffic of their spill scratch
+    // measured on C2 (profiles/README.md, round 2): 256 threads per individual with 3-4 resident CTAs per SM is the best of the swept
+    // configurations; throughput does not grow with more resident CTAs (the per-individual time grows in proportion)
     switch (nt) {
         case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
         case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
         case 128: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
-        default: return launch_forward_t<256, 256, 4>(p, grid, st, occ);
+        default: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
     }
 }
 
@@ -478,7 +478,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             CK(cudaMemcpy(&cur, ctx->d_cursor.p, sizeof cur, cudaMemcpyDeviceToHost));
             const int consumers = done + kb_fail + std::min<int>((int) again.size() - kb_fail, slots);
             if (consumers > 0 && cur > 0 && !big_mode) {
-                const double est = 1.2 * (double) cur / consumers;
+                const double est = 1.06 * (double) cur / consumers;
                 double &e = ctx->est_units[estep ? 1 : 0];
                 e = (done + kb_fail == n_wave) ? std::max(est, 0.5 * e) : std::max(est, e);      // everything fitted: follow the estimate down slowly
             }

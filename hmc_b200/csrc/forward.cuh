@@ -75,7 +75,7 @@ struct HashTab {
 
 template <int NT, int CC>
 struct FwdSmem {
-    static constexpr int HC = 2 * CC <= 256 ? 256 : 2 * CC <= 512 ? 512 : 2 * CC <= 1024 ? 1024 : 2 * CC <= 2048 ? 2048 : 4096;   // power of two >= 2 CC
+    static constexpr int HC = ((CC + CC / 4 + CC / 16 + 63) >> 6) << 6;     // hash slots of a step with CC candidates (see hsize)
     u64 keys[HC];
     double tpv[HC];
     u32 ord[HC], cnt[HC], soff[HC];
@@ -247,27 +247,49 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         if (head_len < L) { nx_word = geno_word(head_len); nx_info = pn.linfo[head_len]; }
 
         // ---------------- locus steps ----------------
+        // The step is written for a SMALL instruction footprint: one instantiation (shared-memory or spill arrays chosen at run time,
+        // generic addressing), no unrolled per-lane batches -- the kernel is instruction-fetch bound otherwise (profiles/README.md:
+        // the GPC-level instruction cache ran at 87 % of its request rate with the 130 KB body of the first round-2 version).
+#pragma unroll 1
         for (int i = head_len; i < L && S_in > 0; ++i) {
             PASS_MARK(7);
             const int g0 = (int) (nx_word & gmask) - 1, g1 = (int) ((nx_word >> gbits) & gmask) - 1;
             const int nA = (int) (nx_info & 0xFF);
             const u32 am = nx_info >> 8;
             if (i + 1 < L) { nx_word = geno_word(i + 1); nx_info = pn.linfo[i + 1]; }
-            // allele-pair groups in the reference's extendAll order (HaploBuilder.cpp:48-79)
-            int ng = 0, C = 0;
-            auto add_group = [&](int x, int y) {
-                if (tid == 0) { sm.gx[ng] = x; sm.gy[ng] = y; sm.gbase[ng] = C; }
-                C += S_in * (x != y ? 2 : 1);
-                ++ng;
-            };
-            if (g0 < 0 && g1 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) for (int k = j; k < nA; ++k) if ((am >> k) & 1u) add_group(j, k); }
-            else if (g0 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g1); }
-            else if (g1 < 0) { for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, g0); }
-            else add_group(g0, g1);
-            if (tid == 0) { sm.gbase[ng] = C; sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; sm.ints[7] = 0; }
+            // allele-pair groups in the reference's extendAll order (HaploBuilder.cpp:48-79): one group at a typed locus; at a locus with
+            // missing alleles thread 0 lists them
+            int ng = 1, C = S_in * (g0 != g1 ? 2 : 1);
+            if (g0 >= 0 && g1 >= 0) {
+                if (tid == 0) { sm.gx[0] = g0; sm.gy[0] = g1; sm.gbase[0] = 0; sm.gbase[1] = C; }
+            }
+            else {
+                if (tid == 0) {
+                    int n = 0, c = 0;
+                    auto add_group = [&](int x, int y) { sm.gx[n] = x; sm.gy[n] = y; sm.gbase[n] = c; c += S_in * (x != y ? 2 : 1); ++n; };
+                    if (g0 < 0 && g1 < 0) {
+#pragma unroll 1
+                        for (int j = 0; j < nA; ++j) {
+                            if (!((am >> j) & 1u)) continue;
+#pragma unroll 1
+                            for (int k = j; k < nA; ++k) if ((am >> k) & 1u) add_group(j, k);
+                        }
+                    }
+                    else {
+                        const int known = g0 < 0 ? g1 : g0;
+#pragma unroll 1
+                        for (int j = 0; j < nA; ++j) if ((am >> j) & 1u) add_group(j, known);
+                    }
+                    sm.gbase[n] = c; sm.ints[1] = n;
+                }
+                block_sync<NT>();
+                ng = sm.ints[1]; C = sm.gbase[ng];
+            }
+            if (tid == 0) { sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; sm.ints[7] = 0; }
             if (tid < 8) sm.look[tid] = 0;
-            int hsize = 64;
-            while (hsize * 4 < 5 * C) hsize <<= 1;     // load factor <= 0.8 even if every candidate were a new state
+            // hash size: 1.3 C slots (load <= 0.77 even if every candidate were a new state, ~0.45 typically), NOT rounded to a power of
+            // two: the slots a step touches lie 2-3x denser, and the spill hash of all resident CTAs has to live in L2 between passes
+            const int hsize = ((C + C / 4 + C / 16 + 63) >> 6) << 6;
             const bool fast = (C <= CC);
             if (!fast && (C > sc.ccap || hsize > sc.hcap)) { status = ST_TOO_BIG; break; }
             if (!fast) ++c_spill;
@@ -278,20 +300,17 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
             int S_out = 0, new_exp = cur_exp;
             long long new_off = 0;
-
-            // The step body; FAST selects shared-memory work arrays (compile-time, so the accesses are LDS/STS/ATOMS).
-            // returns 0 = ok, 1 = every extension died, 2 = status set (the hash slots were reset)
-            auto body = [&](auto fast_tag) -> int {
-                constexpr bool FAST = decltype(fast_tag)::value;
+            int rc = 0;         // 0 = ok, 1 = every extension died, 2 = status set (the hash arrays were reset)
+            do {
                 HashTab tab;
-                tab.keys = FAST ? sm.keys : sc.keys; tab.tpvs = FAST ? sm.tpv : sc.tpv; tab.ord = FAST ? sm.ord : sc.ord;
-                tab.cnt = FAST ? sm.cnt : sc.cnt; tab.soffs = FAST ? sm.soff : sc.soff;
-                int *const cand = FAST ? sm.cand : sc.cand;
-                int *const sarr = FAST ? sm.sarr : sc.sarr;
-                int2 *const mlist = FAST ? sm.mlist : sc.mlist;
-                const int mcap = FAST ? (CC / 2 + 1) : sc.scap;
-                const u32 hmask = (u32) hsize - 1u;
-                auto reset_table = [&]() {      // error exits: leave the hash slots all-empty for the next individual
+                tab.keys = fast ? sm.keys : sc.keys; tab.tpvs = fast ? sm.tpv : sc.tpv; tab.ord = fast ? sm.ord : sc.ord;
+                tab.cnt = fast ? sm.cnt : sc.cnt; tab.soffs = fast ? sm.soff : sc.soff;
+                int *const cand = fast ? sm.cand : sc.cand;
+                int *const sarr = fast ? sm.sarr : sc.sarr;
+                int2 *const mlist = fast ? sm.mlist : sc.mlist;
+                const int mcap = fast ? (CC / 2 + 1) : sc.scap;
+                const u32 hsz = (u32) hsize;
+                auto reset_table = [&]() {      // error exits: leave the hash arrays all-empty for the next individual
                     block_sync<NT>();
 #pragma unroll 1
                     for (int h = tid; h < hsize; h += NT) tab.release((u32) h);
@@ -299,12 +318,11 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
                 // input state views
                 const BlockLayout bli = block_layout(S_in, 0, p.estep);
-                const int *gi_ida = (const int *) (arena + cur_off + bli.ida), *gi_idb = (const int *) (arena + cur_off + bli.idb);
-                const double *gi_alpha = (const double *) (arena + cur_off + bli.alpha);
-                const double *gi_v1 = (const double *) (arena + cur_off + bli.v1);
-                const bool in_cache = FAST || S_in <= CC;       // FAST implies S_in <= C <= CC
-                const int *const in_ida = in_cache ? sm.ida[par] : gi_ida, *const in_idb = in_cache ? sm.idb[par] : gi_idb;
-                const double *const in_alpha = in_cache ? sm.alpha[par] : gi_alpha, *const in_v1 = in_cache ? sm.v1[par] : gi_v1;
+                const bool in_cache = S_in <= CC;
+                const int *const in_ida = in_cache ? sm.ida[par] : (const int *) (arena + cur_off + bli.ida);
+                const int *const in_idb = in_cache ? sm.idb[par] : (const int *) (arena + cur_off + bli.idb);
+                const double *const in_alpha = in_cache ? sm.alpha[par] : (const double *) (arena + cur_off + bli.alpha);
+                const double *const in_v1 = in_cache ? sm.v1[par] : (const double *) (arena + cur_off + bli.v1);
 
                 // forward-link block of index i (E-step mode)
                 long long fwd_off = 0;
@@ -313,29 +331,33 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 PASS_MARK(0);
                 if (estep) {
                     fwd_off = sm.ll[1];
-                    if (fwd_off < 0) { status = ST_NOMEM; return 2; }       // nothing inserted yet: the hash slots are clean
+                    if (fwd_off < 0) { status = ST_NOMEM; rc = 2; break; }       // nothing inserted yet: the hash arrays are clean
                     if (tid == 0) { rec[i].fwd_off = fwd_off; rec[i].fwd_slots = C; }
                 }
                 int *fwd = (int *) (arena + fwd_off);
 
                 auto decode = [&](int c, int &g, int &s, int &dir) {
                     g = 0;
+#pragma unroll 1
                     while (g + 1 < ng && c >= sm.gbase[g + 1]) ++g;
                     const int r = c - sm.gbase[g];
                     if (sm.gx[g] != sm.gy[g]) { s = r >> 1; dir = r & 1; } else { s = r; dir = 0; }
                 };
 
                 // ---- pass A: lanes over predecessor states; gather successors, canonicalise, hash-insert ----
+                // (two states per lane and round -- four compare-and-swaps in flight -- was measured: 18 % SLOWER; the inserts do not overlap)
                 int my_new = 0, my_arr = 0;
                 {
                     int nx_pa = 0, nx_pb = 0;
                     double nx_al = 0.0;
                     if (tid < S_in) { nx_pa = in_ida[tid]; nx_pb = in_idb[tid]; nx_al = in_alpha[tid]; }
+#pragma unroll 1
                     for (int s = tid; s < S_in; s += NT) {
                         const int pa = nx_pa, pb = nx_pb;
                         const bool alive = nx_al > 0.0;       // HaploBuilder.cpp:237
                         if (s + NT < S_in) { nx_pa = in_ida[s + NT]; nx_pb = in_idb[s + NT]; nx_al = in_alpha[s + NT]; }      // next round's state, one round ahead
                         const int4 *ra = succ16 + (size_t) pa * A, *rb = succ16 + (size_t) pb * A;
+#pragma unroll 1
                         for (int g = 0; g < ng; ++g) {
                             const int x = sm.gx[g], y = sm.gy[g];
                             const bool het = x != y;
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                                     tv[d] = __dmul_rn(__hiloint2double(ea[d].w, ea[d].z), __hiloint2double(eb[d].w, eb[d].z));
                                     if (hpa > hpb) { const int t = hpa; hpa = hpb; hpb = t; rev[d] = 1; }
                                     key[d] = ((u64) (u32) hpa << 32) | (u32) hpb;
-                                    hh[d] = mix64(key[d]) & hmask;
+                                    hh[d] = __umulhi(mix64(key[d]), hsz);
                                     prev[d] = atomicCAS(tab.keys + hh[d], KEY_EMPTY, key[d]);
                                 }
                             }
@@ -373,10 +395,11 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                                 if (ok[d]) {
                                     u32 h = hh[d];
                                     u64 pv = prev[d];
+#pragma unroll 1
                                     for (;;) {
                                         if (pv == KEY_EMPTY) { tab.tpvs[h] = tv[d]; ++my_new; break; }
                                         if (pv == key[d]) break;
-                                        h = (h + 1) & hmask;
+                                        h = (h + 1 == hsz) ? 0u : h + 1;
                                         pv = atomicCAS(tab.keys + h, KEY_EMPTY, key[d]);
                                     }
                                     atomicMin(tab.ord + h, (u32) (c0 + d));
@@ -398,22 +421,23 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 PASS_MARK(1);
                 S_out = sm.ints[4];
                 const int n_arr = sm.ints[5];
-                if (S_out == 0) return 1;       // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82 (nothing was inserted)
-                if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; reset_table(); return 2; }
+                if (S_out == 0) { rc = 1; break; }      // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82 (nothing was inserted)
+                if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; reset_table(); rc = 2; break; }
                 if (tid == 0) sm.ll[1] = alloc(block_layout(S_out, n_arr, p.estep).total);
                 block_sync<NT>();
                 new_off = sm.ll[1];
-                if (new_off < 0) { status = ST_NOMEM; reset_table(); return 2; }
+                if (new_off < 0) { status = ST_NOMEM; reset_table(); rc = 2; break; }
                 c_arr += n_arr;
 
                 const BlockLayout blo = block_layout(S_out, n_arr, p.estep);
-                int *t_ida = (int *) (arena + new_off + blo.ida), *t_idb = (int *) (arena + new_off + blo.idb);
-                double *t_alpha = (double *) (arena + new_off + blo.alpha);
-                double *t_v1 = (double *) (arena + new_off + blo.v1);
-                unsigned char *t_ab = (unsigned char *) (arena + new_off + blo.ab);
-                int *t_aoff = (int *) (arena + new_off + blo.aoff);
-                u32 *t_arr = (u32 *) (arena + new_off + blo.arr);
-                double *t_tp = (double *) (arena + new_off + blo.tp);
+                u64 *const oblk = arena + new_off;
+                int *t_ida = (int *) (oblk + blo.ida), *t_idb = (int *) (oblk + blo.idb);
+                double *t_alpha = (double *) (oblk + blo.alpha);
+                double *t_v1 = (double *) (oblk + blo.v1);
+                unsigned char *t_ab = (unsigned char *) (oblk + blo.ab);
+                int *t_aoff = (int *) (oblk + blo.aoff);
+                u32 *t_arr = (u32 *) (oblk + blo.arr);
+                double *t_tp = (double *) (oblk + blo.tp);
                 int *co_ida = sm.ida[par ^ 1], *co_idb = sm.idb[par ^ 1];
                 double *co_alpha = sm.alpha[par ^ 1], *co_v1 = sm.v1[par ^ 1];
                 const bool out_cache = S_out <= CC;
@@ -421,41 +445,26 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 if (!estep && tid == 0) t_aoff[S_out] = n_arr;
 
                 // ---- pass C: creators in ordinal order -> state indices and arrival offsets; single-arrival states are finished here ----
-                // a lane owns 4 consecutive ordinals of a 128-candidate tile: the slot loads of a tile are 4-deep per lane and one look-back serves 128
+                // a warp takes 32 consecutive ordinals per tile; the (creators, arrivals) prefixes of the tiles are chained through the look-back ring
                 {
-                    const int ntiles = (C + 127) >> 7;
+                    const int ntiles = (C + 31) >> 5;
+                    const u32 lt_mask = (1u << lane) - 1u;
+#pragma unroll 1
                     for (int tile = wid; tile < ntiles; tile += NW) {
-                        const int c0 = (tile << 7) + lane * 4;
-                        int enc[4];
-                        if (c0 + 4 <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
-                        else {
+                        const int c = (tile << 5) + lane;
+                        const int enc = (c < C) ? cand[c] : -1;
+                        const u32 h = (u32) enc & SLOT_MASK;
+                        u32 so = 0xFFFFFFFFu, sn = 0;
+                        u64 key = 0;
+                        double tv = 0.0;
+                        if (enc >= 0) { so = tab.ord[h]; sn = tab.cnt[h]; key = tab.keys[h]; tv = tab.tpvs[h]; }       // four loads, one trip
+                        const bool cr = enc >= 0 && so == (u32) c;
+                        const int nn = cr ? (int) sn : 0;
+                        const u32 crm = __ballot_sync(FULL, cr);
+                        int xa = nn;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
-                        }
-                        // the slot of every candidate: four independent loads each, one trip
-                        u64 skey[4];
-                        double stv[4];
-                        u32 sord[4], scnt[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            skey[u] = 0; stv[u] = 0.0; sord[u] = 0xFFFFFFFFu; scnt[u] = 0;
-                            if (enc[u] >= 0) { const u32 h = (u32) enc[u] & SLOT_MASK; sord[u] = tab.ord[h]; scnt[u] = tab.cnt[h]; skey[u] = tab.keys[h]; stv[u] = tab.tpvs[h]; }
-                        }
-                        int ncr = 0, nar = 0;
-                        bool cr[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            cr[u] = enc[u] >= 0 && sord[u] == (u32) (c0 + u);
-                            ncr += cr[u] ? 1 : 0;
-                            nar += cr[u] ? (int) scnt[u] : 0;
-                        }
-                        int xs = ncr, xa = nar;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int ys = __shfl_up_sync(FULL, xs, o), ya = __shfl_up_sync(FULL, xa, o);
-                            if (lane >= o) { xs += ys; xa += ya; }
-                        }
-                        const int tot_cr = __shfl_sync(FULL, xs, 31), tot_ar = __shfl_sync(FULL, xa, 31);
+                        for (int o = 1; o < 32; o <<= 1) { const int ya = __shfl_up_sync(FULL, xa, o); if (lane >= o) xa += ya; }
+                        const int tot_ar = __shfl_sync(FULL, xa, 31);
                         unsigned long long prevp = 0;
                         if (lane == 0) {
                             if (tile > 0) {
@@ -465,50 +474,46 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             }
                             const unsigned long long b_idx = (prevp >> 24) & 0xFFFFFFull, b_off = prevp & 0xFFFFFFull;
                             *(volatile unsigned long long *) &sm.look[tile & 7] =
-                                ((unsigned long long) ((tile + 1) & 0xFFFF) << 48) | ((b_idx + (unsigned long long) tot_cr) << 24) | (b_off + (unsigned long long) tot_ar);
+                                ((unsigned long long) ((tile + 1) & 0xFFFF) << 48) | ((b_idx + (unsigned long long) __popc(crm)) << 24) | (b_off + (unsigned long long) tot_ar);
                         }
                         prevp = __shfl_sync(FULL, prevp, 0);
-                        int idx = (int) ((prevp >> 24) & 0xFFFFFFull) + xs - ncr;
-                        int off = (int) (prevp & 0xFFFFFFull) + xa - nar;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (!cr[u]) continue;
-                            const int c = c0 + u;
-                            const u32 h = (u32) enc[u] & SLOT_MASK;
-                            const u32 rev = ((u32) enc[u] >> 30) & 1u;
-                            const u64 key = skey[u];
-                            const double tv = stv[u];
-                            const int nn = (int) scnt[u];
-                            int g, s, dir;
-                            decode(c, g, s, dir);
-                            const int gxv = sm.gx[g], gyv = sm.gy[g];
-                            const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
-                            const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
-                            ST_OUT(t_ida + idx, hpa); ST_OUT(t_idb + idx, hpb);
-                            ST_OUT(t_ab + idx, (unsigned char) ((rev ? yy : xx) | ((rev ? xx : yy) << 4)));
-                            if (estep) ST_OUT(t_tp + idx, tv); else ST_OUT(t_aoff + idx, off);
-                            if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; }
-                            if (nn == 1) {
-                                const double alpha = __dmul_rn(in_alpha[s], tv);
-                                ST_OUT(t_alpha + idx, alpha);
-                                if (out_cache) co_alpha[idx] = alpha;
-                                amax = fmax(amax, alpha);
-                                if (!estep) {
-                                    const double v = __dmul_rn(in_v1[s], tv);
-                                    ST_OUT(t_v1 + idx, v);
-                                    if (out_cache) co_v1[idx] = v;
-                                    ST_OUT(t_arr + off, (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u));
-                                }
-                                else fwd[c] = (int) ((u32) idx | (rev << 31));
-                                tab.release(h);
-                                cand[c] = -1;
+                        if (!cr) continue;
+                        const int idx = (int) ((prevp >> 24) & 0xFFFFFFull) + __popc(crm & lt_mask);
+                        const int off = (int) (prevp & 0xFFFFFFull) + xa - nn;
+                        const u32 rev = ((u32) enc >> 30) & 1u;
+                        int g, s, dir;
+                        decode(c, g, s, dir);
+                        const int gxv = sm.gx[g], gyv = sm.gy[g];
+                        const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
+                        const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
+                        ST_OUT(t_ida + idx, hpa); ST_OUT(t_idb + idx, hpb);
+                        ST_OUT(t_ab + idx, (unsigned char) ((rev ? yy : xx) | ((rev ? xx : yy) << 4)));
+                        if (estep) ST_OUT(t_tp + idx, tv); else ST_OUT(t_aoff + idx, off);
+                        if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; }
+#ifndef FWD_NO_PREFETCH
+                        // the next step gathers the successor rows of this state: start moving them to L2 now (a row of a biallelic model is one sector)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(succ16 + (size_t) hpa * A));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(succ16 + (size_t) hpb * A));
+#endif
+                        if (nn == 1) {
+                            const double alpha = __dmul_rn(in_alpha[s], tv);
+                            ST_OUT(t_alpha + idx, alpha);
+                            if (out_cache) co_alpha[idx] = alpha;
+                            amax = fmax(amax, alpha);
+                            if (!estep) {
+                                const double v = __dmul_rn(in_v1[s], tv);
+                                ST_OUT(t_v1 + idx, v);
+                                if (out_cache) co_v1[idx] = v;
+                                ST_OUT(t_arr + off, (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u));
                             }
-                            else {
-                                tab.created(h, (u32) idx, (u32) off);     // ord = state index (never equals an ordinal), cnt = 0 (the scatter counts again), soff
-                                if (nn <= 8) mlist[atomicAdd(&sm.ints[6], 1)] = make_int2(idx, (int) h);
-                                else mlist[mcap - 1 - atomicAdd(&sm.ints[7], 1)] = make_int2(idx, (int) h);
-                            }
-                            ++idx; off += nn;
+                            else fwd[c] = (int) ((u32) idx | (rev << 31));
+                            tab.release(h);
+                            cand[c] = -1;
+                        }
+                        else {
+                            tab.created(h, (u32) idx, (u32) off);     // ord = state index (never equals an ordinal), cnt = 0 (the scatter counts again), soff
+                            if (nn <= 8) mlist[atomicAdd(&sm.ints[6], 1)] = make_int2(idx, (int) h);
+                            else mlist[mcap - 1 - atomicAdd(&sm.ints[7], 1)] = make_int2(idx, (int) h);
                         }
                     }
                 }
@@ -518,39 +523,23 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 
                 // ---- pass D: scatter the arrivals of multi-arrival states (unordered inside a segment; ordered in E) ----
                 if (n_light + n_heavy > 0) {
-                    for (int base = 0; base < C; base += NT * 4) {
-                        const int c0 = base + tid * 4;
-                        int enc[4];
-                        if (c0 + 4 <= C) { const int4 e4 = *reinterpret_cast<const int4 *>(cand + c0); enc[0] = e4.x; enc[1] = e4.y; enc[2] = e4.z; enc[3] = e4.w; }
-                        else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) enc[u] = (c0 + u < C) ? cand[c0 + u] : -1;
-                        }
-                        u32 so[4], pos[4], ov[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            so[u] = 0; pos[u] = 0; ov[u] = 0;
-                            if (enc[u] >= 0) {
-                                const u32 h = (u32) enc[u] & SLOT_MASK;
-                                so[u] = tab.soffs[h];
-                                pos[u] = atomicAdd(tab.cnt + h, 1u);
-                                if (estep) ov[u] = tab.ord[h];
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (enc[u] >= 0) {
-                                const u32 rev = ((u32) enc[u] >> 30) & 1u;
-                                sarr[so[u] + pos[u]] = (int) ((u32) (c0 + u) | (rev << 31));
-                                if (estep) fwd[c0 + u] = (int) ((ov[u] & 0x7FFFFFFFu) | (rev << 31));
-                            }
+#pragma unroll 1
+                    for (int c = tid; c < C; c += NT) {
+                        const int enc = cand[c];
+                        if (enc >= 0) {
+                            const u32 h = (u32) enc & SLOT_MASK, rev = ((u32) enc >> 30) & 1u;
+                            const u32 so = tab.soffs[h];
+                            const u32 pos = atomicAdd(tab.cnt + h, 1u);
+                            sarr[so + pos] = (int) ((u32) c | (rev << 31));
+                            if (estep) fwd[c] = (int) ((tab.ord[h] & 0x7FFFFFFFu) | (rev << 31));
                         }
                     }
                     block_sync<NT>();
                 }
                 PASS_MARK(3);
 
-                // ---- pass E (light): one lane per state with 2..8 arrivals, ordered in registers ----
+                // ---- pass E (light): one lane per state with 2..8 arrivals: ordinals ordered in registers, then taken one by one ----
+#pragma unroll 1
                 for (int m = tid; m < n_light; m += NT) {
                     const int2 me = mlist[m];
                     const int idx = me.x;
@@ -573,17 +562,18 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     }
                     else cx(0, 1);
                     double alpha = 0.0, vmax = 0.0;
+#pragma unroll 1
+                    for (int q = 0; q < n; ++q) {
+                        const int e = v[0];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (q < n) {
-                            int g, s, dir;
-                            decode(v[q] & 0x7FFFFFFF, g, s, dir);
-                            const double term = __dmul_rn(in_alpha[s], tv);
-                            alpha = (q == 0) ? term : __dadd_rn(alpha, term);
-                            if (!estep) {
-                                vmax = fmax(vmax, in_v1[s]);
-                                ST_OUT(t_arr + a0 + q, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) v[q] >> 31) ? ARR_REV : 0u));
-                            }
+                        for (int r = 0; r < 7; ++r) v[r] = v[r + 1];       // (static register indexing: the list slides down)
+                        int g, s, dir;
+                        decode(e & 0x7FFFFFFF, g, s, dir);
+                        const double term = __dmul_rn(in_alpha[s], tv);
+                        alpha = (q == 0) ? term : __dadd_rn(alpha, term);
+                        if (!estep) {
+                            vmax = fmax(vmax, in_v1[s]);
+                            ST_OUT(t_arr + a0 + q, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
                         }
                     }
                     ST_OUT(t_alpha + idx, alpha);
@@ -596,6 +586,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     }
                 }
                 // ---- pass E (heavy): one warp per state with more than 8 arrivals (about 1 % of the states); rank by counting, ordered copy in `cand` (free after D) ----
+#pragma unroll 1
                 for (int m = wid; m < n_heavy; m += NW) {
                     const int2 me = mlist[mcap - 1 - m];
                     const int idx = me.x;
@@ -604,18 +595,22 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                     const int a0 = (int) tab.soffs[h], n = (int) tab.cnt[h];
                     __syncwarp();
                     if (lane == 0) tab.release(h);
+#pragma unroll 1
                     for (int b0 = 0; b0 < n; b0 += 32) {
                         const int mine = (b0 + lane < n) ? sarr[a0 + b0 + lane] : 0x7FFFFFFF;
                         int rank = 0;
+#pragma unroll 1
                         for (int q0 = 0; q0 < n; q0 += 32) {
                             const int other = (q0 + lane < n) ? sarr[a0 + q0 + lane] : 0x7FFFFFFF;
                             const int lim = min(32, n - q0);
+#pragma unroll 1
                             for (int j = 0; j < lim; ++j) rank += ((__shfl_sync(FULL, other, j) & 0x7FFFFFFF) < (mine & 0x7FFFFFFF)) ? 1 : 0;
                         }
                         if (b0 + lane < n) cand[a0 + rank] = mine;
                     }
                     __syncwarp();
                     double alpha = 0.0, vmax = 0.0;
+#pragma unroll 1
                     for (int b0 = 0; b0 < n; b0 += 32) {
                         double term = 0.0;
                         if (b0 + lane < n) {
@@ -629,6 +624,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                             }
                         }
                         const int lim = min(32, n - b0);
+#pragma unroll 1
                         for (int j = 0; j < lim; ++j) {
                             const double tj = __shfl_sync(FULL, term, j);
                             alpha = (b0 + j == 0) ? tj : __dadd_rn(alpha, tj);
@@ -656,10 +652,12 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                         if (lane == 0) sm.red[wid] = amax;
                         __syncthreads();
                         amax = 0.0;
+#pragma unroll 1
                         for (int q = 0; q < NW; ++q) amax = fmax(amax, sm.red[q]);
                     }
                     if (amax > 0.0 && amax < 0x1p-512) {
                         block_sync<NT>();
+#pragma unroll 1
                         for (int idx = tid; idx < S_out; idx += NT) {
                             const double a2 = t_alpha[idx] * 0x1p+512;
                             t_alpha[idx] = a2;
@@ -673,9 +671,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                         new_exp += 512;
                     }
                 }
-                return 0;
-            };
-            const int rc = fast ? body(std::true_type()) : body(std::false_type());
+            } while (false);
             if (rc == 1) { S_in = 0; break; }
             if (rc == 2) break;
             if (tid == 0) {

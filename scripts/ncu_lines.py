@@ -5,7 +5,7 @@ import csv, io, os, re, subprocess, sys, tempfile
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "hmc_b200", "libhmc_b200.so")
+so = os.environ.get("HMC_B200_LIB") or os.path.join(root, "hmc_b200", "libhmc_b200.so")
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
