@@ -258,15 +258,13 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
 #ifdef FWD_SWEEP
     if (const char *env = getenv("HMC_B200_FWD_CFG")) {     // kernel-configuration experiments
         switch (atoi(env)) {
-            case 0: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
-            case 1: return launch_forward_t<128, 256, 6>(p, grid, st, occ);
-            case 2: return launch_forward_t<128, 128, 8>(p, grid, st, occ);
-            case 3: return launch_forward_t<128, 128, 10>(p, grid, st, occ);
-            case 4: return launch_forward_t<256, 128, 5>(p, grid, st, occ);
-            case 5: return launch_forward_t<64, 128, 16>(p, grid, st, occ);
-            case 6: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
-            case 7: return launch_forward_t<512, 512, 2>(p, grid, st, occ);
-            case 8: return launch_forward_t<64, 64, 20>(p, grid, st, occ);
+            case 0: return launch_forward_t<256, 256, 3>(p, grid, st, occ);
+            case 1: return launch_forward_t<256, 256, 4>(p, grid, st, occ);
+            case 2: return launch_forward_t<256, 128, 4>(p, grid, st, occ);
+            case 3: return launch_forward_t<256, 128, 3>(p, grid, st, occ);
+            case 4: return launch_forward_t<128, 128, 5>(p, grid, st, occ);
+            case 5: return launch_forward_t<128, 128, 4>(p, grid, st, occ);
+            case 6: return launch_forward_t<384, 256, 2>(p, grid, st, occ);
             default: break;
         }
     }
@@ -277,7 +275,7 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
         case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
         case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
         case 128: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
-        default: return launch_forward_t<256, 512, 3>(p, grid, st, occ);
+        default: return launch_forward_t<256, 256, 3>(p, grid, st, occ);
     }
 }
 

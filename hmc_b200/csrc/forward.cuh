@@ -33,6 +33,10 @@
 
 #include <type_traits>
 
+#ifndef FWD_SMEM_KEYS
+#define FWD_SMEM_KEYS 2048
+#endif
+
 #include "common.cuh"
 
 namespace hmc {
@@ -76,7 +80,11 @@ struct HashTab {
 template <int NT, int CC>
 struct FwdSmem {
     static constexpr int HC = ((CC + CC / 4 + CC / 16 + 63) >> 6) << 6;     // hash slots of a step with CC candidates (see hsize)
-    u64 keys[HC];
+    // The KEYS of the hash stay in shared memory for steps of up to ~1,550 candidates (KB slots), far beyond the fast path: the insert's
+    // compare-and-swap is the one access of the step a warp has to wait for slot by slot (probe chains), and on the L2-resident spill
+    // hash it was a third of all warp time; the other slot fields of such a step live in the global scratch (reductions / later passes).
+    static constexpr int KB = FWD_SMEM_KEYS;
+    u64 keys[KB > HC ? KB : HC];
     double tpv[HC];
     u32 ord[HC], cnt[HC], soff[HC];
     double alpha[2][CC], v1[2][CC];
@@ -111,7 +119,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
     const int4 *const succ16 = reinterpret_cast<const int4 *>(md.succ16);
 
     if (tid == 0) { sm.ll[2] = 0; sm.ll[3] = 0; }
-    for (int h = tid; h < Smem::HC; h += NT) { sm.keys[h] = KEY_EMPTY; sm.ord[h] = 0xFFFFFFFFu; sm.cnt[h] = 0; }
+    for (int h = tid; h < Smem::HC; h += NT) { sm.ord[h] = 0xFFFFFFFFu; sm.cnt[h] = 0; }
+    for (int h = tid; h < (Smem::KB > Smem::HC ? Smem::KB : Smem::HC); h += NT) sm.keys[h] = KEY_EMPTY;
 
     // chunked bump allocation (thread 0 only); returns -1 when the arena is exhausted
     auto alloc = [&](long long units) -> long long {
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             int rc = 0;         // 0 = ok, 1 = every extension died, 2 = status set (the hash arrays were reset)
             do {
                 HashTab tab;
-                tab.keys = fast ? sm.keys : sc.keys; tab.tpvs = fast ? sm.tpv : sc.tpv; tab.ord = fast ? sm.ord : sc.ord;
+                tab.keys = (fast || hsize <= Smem::KB) ? sm.keys : sc.keys; tab.tpvs = fast ? sm.tpv : sc.tpv; tab.ord = fast ? sm.ord : sc.ord;
                 tab.cnt = fast ? sm.cnt : sc.cnt; tab.soffs = fast ? sm.soff : sc.soff;
                 int *const cand = fast ? sm.cand : sc.cand;
                 int *const sarr = fast ? sm.sarr : sc.sarr;

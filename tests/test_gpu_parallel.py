@@ -77,7 +77,7 @@ def test_two_ranks_equal_one(name, mode):
     procs = [ctx.Process(target=_worker, args=(r, world, port, name, q, backend, device_collectives)) for r in range(world)]
     for p in procs:
         p.start()
-    out = sorted(q.get(timeout=180) for _ in range(world))
+    out = sorted(q.get(timeout=420) for _ in range(world))
     assert all(o[1] != "error" for o in out), [o[2] for o in out if o[1] == "error"]
     for p in procs:
         p.join(timeout=60)
