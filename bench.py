@@ -398,10 +398,12 @@ def run_ours(args):
 
 
 def kernel_sources_sha1() -> str:
+    """Identity of the kernels the roofline is quoted on (forward K1 + K-best K2): profiles/forward_traffic.json carries the hash of the
+    sources its ncu capture was taken from and is only used while they are unchanged."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "hmc_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in ("common.cuh", "forward.cuh", "kbest.cuh"):
         h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()
 

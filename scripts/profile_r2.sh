@@ -1,0 +1,14 @@
+#!/bin/bash
+# round-2 evidence: bench line, launch list of the bench command, full captures of the forward and the K-best kernel (bench command)
+cd $GRAFT_REPO_ROOT
+make -C oracle -s
+python bench.py --steps 5 --warmup 3 > gpurun_out/r2_final_bench_N1.json 2> gpurun_out/r2_final_bench.err || exit 1
+CMD="python bench.py --steps 2 --warmup 1"
+export HMC_BENCH_EPASS_REPS=1
+$CMD > gpurun_out/plain_f.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_final_bench_launches.csv $CMD > gpurun_out/ncu_f1.log 2>&1
+export HMC_BENCH_SKIP_EPASS=1
+ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s 2 -c 1 -o gpurun_out/r2_final_forward_full $CMD > gpurun_out/ncu_f2.log 2>&1
+tail -1 gpurun_out/ncu_f2.log
+ncu --set full --clock-control none --import-source on -k regex:kbest_kernel -s 2 -c 1 -o gpurun_out/r2_final_kbest_full $CMD > gpurun_out/ncu_f3.log 2>&1
+tail -1 gpurun_out/ncu_f3.log
