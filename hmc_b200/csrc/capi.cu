@@ -23,6 +23,7 @@
 #include <atomic>
 #include "kbest.cuh"
 #include "estep.cuh"
+#include "emit.cuh"
 
 using namespace hmc;
 
@@ -68,6 +69,8 @@ struct hmc_ctx {
     int threads_opt = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaStream_t stream2 = nullptr;          // the K-best kernel of a resolve pass runs here, beside the forward kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     // panel
@@ -111,7 +114,7 @@ struct hmc_ctx {
     DevBuf<int> d_flags;                     // [0] exhausted, [1] queue
     DevBuf<long long> d_counters;
     DevBuf<LocusRec> d_loci;
-    DevBuf<int> d_wave, d_status, d_final_exp, d_locus_exp;
+    DevBuf<int> d_wave, d_status, d_final_exp, d_locus_exp, d_done;
     DevBuf<long long> d_cycles;
     DevBuf<u64> d_kb_eoff;
     DevBuf<u32> d_kb_chain, d_kb_stack;
@@ -125,6 +128,11 @@ struct hmc_ctx {
     DevBuf<double> d_pg, d_cov, d_prior, d_post;
     DevBuf<int> d_exp, d_nres;
     DevBuf<signed char> d_haps;
+    DevBuf<double> d_lk;                     // K8: haplotype likelihoods, text emission
+    DevBuf<int> d_emit_sym;
+    DevBuf<unsigned char> d_emit_wid, d_emit_tmp;
+    DevBuf<long long> d_emit_off;
+    DevBuf<char> d_emit_text;
 
     // E-step
     DevBuf<double> d_counts, d_pgin;
@@ -234,12 +242,19 @@ __global__ void succ16_kernel(const int *succ, const double *tp, size_t n, int P
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory carve-out (% of the SM's 228 KB) the forward kernel asks for: what MINB resident CTAs need.  The streamed K-best kernel asks
+// for the same, since CTAs of two kernels only share an SM when their L1 / shared-memory split is the same.
+static thread_local int t_fwd_carveout = 0;
+
 template <int NT, int CC, int MINB, bool ESTEP>
 static cudaError_t launch_forward_e(const FwdParams &p, int grid, cudaStream_t st, int *max_blocks_per_sm)
 {
     auto kern = forward_kernel<NT, CC, MINB, ESTEP>;
     const size_t smem = sizeof(FwdSmem<NT, CC>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    t_fwd_carveout = (int) std::min<size_t>(100, (100 * MINB * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, t_fwd_carveout);
     if (e != cudaSuccess) return e;
     if (max_blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, kern, NT, smem);
     kern<<<grid, NT, smem, st>>>(p);
@@ -346,8 +361,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     const int L = ctx->L;
     int rc = ensure_arena(ctx);
     if (rc) return rc;
-    CK(ctx->d_cursor.ensure(1));
-    CK(ctx->d_flags.ensure(2));
+    CK(ctx->d_cursor.ensure(2));         // [0] forward (and serial K-best), [1] streamed K-best
+    CK(ctx->d_flags.ensure(4));          // [0] arena exhausted, [1] forward queue, [2] K-best queue, [3] done count
     CK(ctx->d_counters.ensure(32));
     ctx->ecache.valid = false;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(long long), ctx->stream));
@@ -364,12 +379,12 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
 
     // wave capacity is bounded by the per-(individual, index) record table
     const size_t max_loci_bytes = (size_t) 6 << 30;
-    int wave_cap = (int) std::min<size_t>((size_t) count, std::max<size_t>(1, max_loci_bytes / ((size_t) (L + 1) * sizeof(LocusRec))));
-    CK(ctx->d_loci.ensure((size_t) wave_cap * (L + 1)));
+    int wave_cap = (int) std::min<size_t>((size_t) count, std::max<size_t>(1, max_loci_bytes / (loci_stride(L) * sizeof(LocusRec))));
+    CK(ctx->d_loci.ensure((size_t) wave_cap * loci_stride(L)));
     CK(ctx->d_wave.ensure(wave_cap));
     CK(ctx->d_status.ensure(wave_cap));
     CK(ctx->d_final_exp.ensure(wave_cap));
-    if (flags & HMC_FLAG_SCALED) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * (L + 1)));
+    if (flags & HMC_FLAG_SCALED) CK(ctx->d_locus_exp.ensure((size_t) wave_cap * exp_stride(L)));
 
     // pending individuals, heaviest first: by the time the previous pass over the same panel spent on them (EM iterations and
     // the E-passes of an M-step resolve the same individuals again and again), else by missing genotypes
@@ -402,14 +417,14 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         if (rc) return rc;
         ctx->h_wave.assign(pending.begin(), pending.begin() + n_wave);
         CK(cudaMemcpyAsync(ctx->d_wave.p, ctx->h_wave.data(), sizeof(int) * n_wave, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_cursor.p, 0, sizeof(unsigned long long), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cursor.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_flags.p, 0, 4 * sizeof(int), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_status.p, 0, sizeof(int) * n_wave, ctx->stream));
 
         fp.panel.N = ctx->N; fp.panel.L = L; fp.panel.Amax = ctx->Amax; fp.panel.bits = ctx->bits; fp.panel.words = ctx->words;
         fp.panel.packed = ctx->d_packed.p; fp.panel.linfo = ctx->d_linfo.p; fp.panel.order = ctx->d_order.p;
         fp.model = ctx->dm;
-        fp.arena.base = ctx->d_arena.p; fp.arena.capacity = estep ? (long long) ctx->d_arena.n : (long long) ((double) ctx->d_arena.n * fwd_share);
+        fp.arena.base = ctx->d_arena.p; fp.arena.capacity = estep ? (long long) ctx->d_arena.n : ((long long) ((double) ctx->d_arena.n * fwd_share) & ~15LL);
         fp.arena.cursor = ctx->d_cursor.p; fp.arena.exhausted = ctx->d_flags.p;
         fp.scratch = pl.desc.p;
         fp.loci = ctx->d_loci.p; fp.wave = ctx->d_wave.p; fp.n_wave = n_wave; fp.K = K; fp.estep = estep;
@@ -421,17 +436,30 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         fp.ind_cycles = nullptr;
         if (getenv("HMC_B200_DEBUG_CYCLES")) { CK(ctx->d_cycles.ensure((size_t) wave_cap * 8)); CK(cudaMemsetAsync(ctx->d_cycles.p, 0, sizeof(long long) * 8 * n_wave, ctx->stream)); fp.ind_cycles = ctx->d_cycles.p; }
 
+        // K2 streamed: the K-best warps are resident beside the forward CTAs and take every individual as the forward kernel finishes it
+        // (done list), so the enumeration hides behind the forward pass instead of following it
+        const bool streamed = !estep && !getenv("HMC_B200_KBEST_SERIAL");
+        fp.done_list = nullptr; fp.done_count = nullptr;
+        if (streamed) {
+            CK(ctx->d_done.ensure((size_t) wave_cap));
+            CK(cudaMemsetAsync(ctx->d_done.p, 0xFF, sizeof(int) * n_wave, ctx->stream));
+            fp.done_list = ctx->d_done.p; fp.done_count = ctx->d_flags.p + 3;
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        }
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         CK(launch_forward(nt, fp, slots, ctx->stream, nullptr));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ++launches;
         if (!estep) {
             // K2: lazy K-best enumeration + traceback, one warp per individual (persistent warps)
-            const int kb_warps = std::min(n_wave, ctx->sms * 16);
-            const int kb_grid = (kb_warps + KB_WARPS - 1) / KB_WARPS;
-            const size_t nw = (size_t) kb_grid * KB_WARPS;
+            // (streamed: at most 8 one-warp CTAs per SM, which even if they all became resident first would leave the forward kernel two CTAs per SM)
+            int kb_warps = std::min(n_wave, ctx->sms * (streamed ? 8 : 16));
+            if (const char *e = getenv("HMC_B200_KB_WARPS")) kb_warps = std::max(1, std::min(kb_warps, atoi(e)));
+            const int kb_per = streamed ? 1 : KB_WARPS;
+            const int kb_grid = (kb_warps + kb_per - 1) / kb_per;
+            const size_t nw = (size_t) kb_grid * kb_per;
             CK(ctx->d_kb_eoff.ensure(nw * (L + 2))); CK(ctx->d_kb_chain.ensure(nw * (L + 2))); CK(ctx->d_kb_stack.ensure(nw * (L + 40)));
-            CK(cudaMemsetAsync(ctx->d_flags.p + 1, 0, sizeof(int), ctx->stream));        // the work queue is reused
+            if (!streamed) CK(cudaMemsetAsync(ctx->d_flags.p + 1, 0, sizeof(int), ctx->stream));        // the work queue is reused
             KbParams kp = {};
             kp.panel = fp.panel; kp.model = fp.model; kp.arena = ctx->d_arena.p; kp.capacity = (long long) ctx->d_arena.n; kp.cursor = ctx->d_cursor.p;
             kp.loci = ctx->d_loci.p; kp.wave = ctx->d_wave.p; kp.status = ctx->d_status.p; kp.final_exp = ctx->d_final_exp.p; kp.locus_exp = fp.locus_exp;
@@ -440,7 +468,17 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             kp.queue = ctx->d_flags.p + 1; kp.work = (unsigned long long *) (ctx->d_counters.p + 24);
             kp.pg = ctx->d_pg.p; kp.cov = ctx->d_cov.p; kp.prior = ctx->d_prior.p; kp.post = ctx->d_post.p; kp.exp2 = ctx->d_exp.p; kp.nres = ctx->d_nres.p;
             kp.haps = ctx->d_haps.p;
-            kbest_kernel<<<kb_grid, KB_WARPS * 32, 0, ctx->stream>>>(kp);
+            if (streamed) {
+                kp.queue = ctx->d_flags.p + 2; kp.done_list = ctx->d_done.p;
+                kp.cursor = ctx->d_cursor.p + 1; kp.region_begin = fp.arena.capacity;      // its own part of the arena: the trellis is still growing
+                CK(cudaFuncSetAttribute(kbest_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, t_fwd_carveout));
+                CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                kbest_kernel<1><<<kb_grid, 32, 0, ctx->stream2>>>(kp);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            }
+            else kbest_kernel<KB_WARPS><<<kb_grid, KB_WARPS * 32, 0, ctx->stream>>>(kp);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -538,6 +576,8 @@ int hmc_ctx_create(hmc_ctx **out, int device, size_t arena_bytes, int threads)
     ctx->device = device; ctx->sms = pr.multiProcessorCount; ctx->arena_req = arena_bytes; ctx->threads_opt = threads;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HMC_ERR_CUDA; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HMC_ERR_CUDA; }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     *out = ctx;
     return HMC_OK;
 }
@@ -553,7 +593,7 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->d_arena.release(); ctx->d_cursor.release(); ctx->d_flags.release(); ctx->d_counters.release(); ctx->d_loci.release();
     ctx->d_wave.release(); ctx->d_status.release(); ctx->d_final_exp.release(); ctx->d_locus_exp.release();
     ctx->pool.mem.release(); ctx->pool.desc.release(); ctx->big_pool.mem.release(); ctx->big_pool.desc.release();
-    ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release();
+    ctx->d_pg.release(); ctx->d_cov.release(); ctx->d_prior.release(); ctx->d_post.release(); ctx->d_exp.release(); ctx->d_nres.release(); ctx->d_haps.release(); ctx->d_lk.release(); ctx->d_emit_sym.release(); ctx->d_emit_wid.release(); ctx->d_emit_tmp.release(); ctx->d_emit_off.release(); ctx->d_emit_text.release();
     ctx->d_counts.release(); ctx->d_pgin.release(); ctx->d_pgexp.release();
     ctx->trie.release(); ctx->d_bexp.release(); ctx->d_eflags.release(); ctx->d_escr.release(); ctx->d_edesc.release(); ctx->d_cycles.release();
     ctx->d_kb_eoff.release(); ctx->d_kb_chain.release(); ctx->d_kb_stack.release();
@@ -562,6 +602,9 @@ void hmc_ctx_destroy(hmc_ctx *ctx)
     ctx->d_af.release(); ctx->d_best_packed.release(); ctx->d_cmp_real.release(); ctx->d_cmp_infer.release(); ctx->d_cmp_out.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -1046,7 +1089,7 @@ int64_t hmc_get_trellis(hmc_ctx *ctx, int individual, int32_t *counts, int64_t c
     if (w < 0) return ctx->fail(HMC_ERR_INVALID, "individual %d is not in the last wave", individual);
     const int L = ctx->L;
     std::vector<LocusRec> rec(L + 1);
-    if (cudaMemcpy(rec.data(), ctx->d_loci.p + (size_t) w * (L + 1), sizeof(LocusRec) * (L + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpy(rec.data(), ctx->d_loci.p + (size_t) w * loci_stride(L), sizeof(LocusRec) * (L + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
         return ctx->fail(HMC_ERR_CUDA, "trellis record copy failed");
     int64_t tot = 0;
     for (int l = 0; l <= L; ++l) {
@@ -1070,3 +1113,4 @@ int64_t hmc_get_trellis(hmc_ctx *ctx, int individual, int32_t *counts, int64_t c
 }  // extern "C"
 
 #include "estep_capi.inl"
+#include "emit_capi.inl"

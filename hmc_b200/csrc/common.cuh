@@ -65,6 +65,11 @@ struct LocusRec {
     long long fwd_off;          // forward-link block (E-step mode)
 };
 
+// Row strides of the per-individual tables [n_wave][L + 1], whole 128-byte lines: the K-best kernel reads the rows of an individual
+// while the forward kernel still writes its neighbours' (streamed mode), and no cached sector may hold data of two individuals.
+__host__ __device__ __forceinline__ size_t loci_stride(int L) { return (size_t) ((L + 1 + 15) & ~15); }      // LocusRec (24 B) x 16 = 3 lines
+__host__ __device__ __forceinline__ size_t exp_stride(int L) { return (size_t) ((L + 1 + 31) & ~31); }       // int x 32 = 1 line
+
 // Arena with chunked bump allocation: a CTA takes CHUNK units at a time and sub-allocates.
 struct Arena {
     u64 *base;
@@ -97,9 +102,10 @@ struct FwdParams {
     int scaled;
     int *status;                // [n_wave]
     int *final_exp;             // [n_wave]
-    int *locus_exp;             // [n_wave][L+1] cumulative exponent (scaled mode) or null
+    int *locus_exp;             // [n_wave][exp_stride(L)] cumulative exponent (scaled mode) or null
     int *queue;                 // work-queue head
     long long *counters;        // steps, states, max_states, arrivals, -, spill steps
+    int *done_list, *done_count; // streamed K-best: every individual the kernel is through with (any status) is appended, in completion order; or null
     long long *work;            // [N] SM cycles the forward kernel spent on every individual it resolved (orders the next pass: longest first)
     long long *ind_cycles;      // [n_wave][8] per-individual diagnostics (cycles, states, ...) or null
 };

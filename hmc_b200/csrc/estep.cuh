@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) backward_kernel(BackParams p)
     if (w >= p.n_wave || p.status[w] != ST_DONE) return;
     const DevPanel &pn = p.panel;
     const int L = pn.L, head_len = p.model.head_len;
-    const LocusRec *rec = p.loci + (size_t) w * (L + 1);
+    const LocusRec *rec = p.loci + (size_t) w * loci_stride(L);
     const u32 *gp = pn.packed + (size_t) p.wave[w] * pn.words;
     int cur_exp = 0;
     {   // index L: beta = 1 (HaploPair.cpp:17,38)
@@ -209,14 +209,14 @@ __global__ void __launch_bounds__(ESTEP_WARPS * 32, ESTEP_MINB) estep_kernel(Est
             for (int j = lane; j < A; j += 32) any |= tr.child[(size_t) root * A + j] >= 0;
             if (!__any_sync(FULL, any)) continue;
         }
-        const LocusRec *rec = p.loci + (size_t) w * (L + 1);
+        const LocusRec *rec = p.loci + (size_t) w * loci_stride(L);
         const int row = p.wave[w] - p.first;
         const double pg = p.pg[row];
         const int pge = p.pg_exp ? p.pg_exp[row] : 0;
         const u32 *gp = pn.packed + (size_t) p.wave[w] * pn.words;
         const int idx0 = start > head_len ? start : head_len;
         const int S0 = rec[idx0].count;
-        const int ea0 = p.aexp ? p.aexp[(size_t) w * (L + 1) + idx0] : 0;
+        const int ea0 = p.aexp ? p.aexp[(size_t) w * exp_stride(L) + idx0] : 0;
         // frame 0: class-0 weight alpha for every state at idx0 (HaploBuilder.cpp:300-305)
         if (S0 > sc.ecap) { if (lane == 0) atomicExch(p.error, 1); continue; }
         if (S0 > 0) {

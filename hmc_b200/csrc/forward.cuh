@@ -36,6 +36,13 @@
 #ifndef FWD_SMEM_KEYS
 #define FWD_SMEM_KEYS 2048
 #endif
+// Register cap of the shipped 256-thread configuration.  Registers are allocated per SM sub-partition (16,384 each): the 6 forward warps a
+// sub-partition holds at 3 CTAs per SM leave 1,024 registers at the 80 ptxas picks on its own (room for a 32-register warp: measured with a
+// probe kernel) and 2,560 at 72, which is one streamed K-best warp at 80 registers beside them.  The cap costs the forward kernel 4 bytes
+// more spill and 1.4 ms on C2; 64 / 64 (two K-best warps per sub-partition) costs it 7 ms.
+#ifndef FWD_MAXNREG
+#define FWD_MAXNREG 72
+#endif
 
 #include "common.cuh"
 
@@ -100,7 +107,7 @@ struct FwdSmem {
 };
 
 template <int NT, int CC, int MINB, bool ESTEP>
-__global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
+__global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG : 255) forward_kernel(FwdParams p)
 {
     typedef FwdSmem<NT, CC> Smem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         constexpr long long CHUNK = 1 << 15;
         units = (units + 1) & ~1LL;
         if (sm.ll[2] + units > sm.ll[3]) {
-            const long long grab = units > CHUNK ? units : CHUNK;
+            const long long grab = units > CHUNK ? ((units + 15) & ~15LL) : CHUNK;       // whole 128-byte lines: see loci_stride
             const unsigned long long base = atomicAdd(p.arena.cursor, (unsigned long long) grab);
             if ((long long) (base + grab) > p.arena.capacity) {
                 atomicAdd(p.arena.cursor, (unsigned long long) (-grab));       // give it back: the K-best kernel allocates behind the trellis
@@ -147,13 +154,17 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         block_sync<NT>();
         const int w = sm.ints[0];
         if (w >= p.n_wave) break;
-        if (sm.ints[3]) { if (tid == 0) p.status[w] = ST_NOMEM; continue; }
+        // hands wave position w to the K-best warps that run beside this kernel (thread 0, after the barrier that ends the individual's last
+        // step: the fence makes the CTA's trellis writes visible before the list entry is)
+        auto publish = [&](int w_) { if (p.done_list) { __threadfence(); atomicExch(p.done_list + atomicAdd(p.done_count, 1), w_); } };
+        if (sm.ints[3]) { if (tid == 0) { p.status[w] = ST_NOMEM; publish(w); } continue; }
+        if (tid == 0) sm.ll[2] = (sm.ll[2] + 15) & ~15LL;       // an individual's blocks start on a fresh 128-byte line (see loci_stride)
         const long long t_begin = clock64();
         long long t_begin_ns = 0;
         if (p.ind_cycles) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); t_begin_ns = (long long) t_; }
         const int ind = p.wave[w];
         const u32 *gp = pn.packed + (size_t) ind * pn.words;
-        LocusRec *rec = p.loci + (size_t) w * (L + 1);
+        LocusRec *rec = p.loci + (size_t) w * loci_stride(L);
 #pragma unroll 1
         for (int l = tid; l <= L; l += NT) { rec[l].count = 0; rec[l].fwd_slots = 0; rec[l].off = 0; rec[l].fwd_off = 0; }
         const int gbits = pn.bits;
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
         }
         block_sync<NT>();
         S_in = sm.ints[1]; status = sm.ints[2]; cur_off = sm.ll[1];
-        if (status != ST_DONE) { if (tid == 0) p.status[w] = status; continue; }
+        if (status != ST_DONE) { if (tid == 0) { p.status[w] = status; publish(w); } continue; }
         {
             const BlockLayout bl = block_layout(S_in, 0, p.estep);
             int *t_ida = (int *) (arena + cur_off + bl.ida), *t_idb = (int *) (arena + cur_off + bl.idb);
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
 #endif
         par = 0;
         long long c_steps = 0, c_states = S_in, c_max = S_in, c_arr = 0, c_spill = 0;
-        if (p.locus_exp && tid == 0) for (int l = 0; l <= head_len; ++l) p.locus_exp[(size_t) w * (L + 1) + l] = 0;
+        if (p.locus_exp && tid == 0) for (int l = 0; l <= head_len; ++l) p.locus_exp[(size_t) w * exp_stride(L) + l] = 0;
 
         // genotype word and locus info of the next step are fetched one step ahead
         u32 nx_word = 0, nx_info = 0;
@@ -685,7 +696,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
             if (rc == 2) break;
             if (tid == 0) {
                 rec[i + 1].off = new_off; rec[i + 1].count = S_out;
-                if (p.locus_exp) p.locus_exp[(size_t) w * (L + 1) + i + 1] = new_exp;
+                if (p.locus_exp) p.locus_exp[(size_t) w * exp_stride(L) + i + 1] = new_exp;
             }
             cur_exp = new_exp;
             ++c_steps; c_states += S_out; if (S_out > c_max) c_max = S_out;
@@ -713,6 +724,7 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(FwdParams p)
                 for (int q = 0; q < 16; ++q) atomicAdd((unsigned long long *) p.counters + 8 + q, (unsigned long long) pass_cyc[q]);
 #endif
             }
+            publish(w);
         }
     }
 }

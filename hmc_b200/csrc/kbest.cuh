@@ -35,7 +35,10 @@ struct KbParams {
     DevModel model;
     u64 *arena;
     long long capacity;             // units of 8 bytes
-    unsigned long long *cursor;     // bump allocator shared with the forward kernel (which has finished)
+    unsigned long long *cursor;     // bump allocator: the forward kernel's own (serial mode: it has finished and the nodes go behind the trellis), or,
+                                    // streamed, a second one over [region_begin, capacity) -- the two kernels give failed grabs back, which is only
+                                    // sound among allocators with the same limit
+    long long region_begin;
     const LocusRec *loci;           // [n_wave][L+1]
     const int *wave;
     int *status;
@@ -48,6 +51,7 @@ struct KbParams {
     u32 *stack;                     // [warps][stack_stride]: node stack of the enumeration (depth <= L + 2); result starts of the all-eager case (K)
     int stack_stride;
     int *queue;
+    const int *done_list;           // streamed mode: wave positions in the order the forward kernel (running beside this one) finishes them, -1 = not yet; or null
     unsigned long long *work;       // [0] lazy-next calls, [1] nodes created, [2] eager list states
     // results, indexed by (panel individual - first)
     double *pg, *cov, *prior, *post;
@@ -56,6 +60,9 @@ struct KbParams {
 };
 
 constexpr int KB_WARPS = 4;
+#ifndef KB1_MAXNREG
+#define KB1_MAXNREG 80      // the streamed one-warp variant: see FWD_MAXNREG (forward.cuh)
+#endif
 constexpr u32 KB_NONE = 0xFFu;
 
 // Node of the lazy enumeration: one visited (index, state).  Byte layout, K-dependent (see kb_node_bytes):
@@ -105,11 +112,14 @@ __host__ __device__ inline EagerLayout eager_layout(int S, int K)
     return e;
 }
 
-__global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
+// WARPS = 4: after the forward kernel, every warp slot of the GPU.  WARPS = 1 (streamed mode): resident BESIDE the forward kernel in the
+// registers its three CTAs per SM leave over (4,096: two warps at 64 registers), fed through done_list as individuals finish.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNREG : 80) kbest_kernel(KbParams p)
 {
     constexpr u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * KB_WARPS + (threadIdx.x >> 5);
+    const int gw = blockIdx.x * WARPS + (threadIdx.x >> 5);
     const DevPanel &pn = p.panel;
     const DevModel &md = p.model;
     const int L = pn.L, K = p.K, head_len = md.head_len;
@@ -125,9 +135,9 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
         units = (units + 7) & ~7LL;
         if (ch_cur + units > ch_end) {
             constexpr long long CHUNK = 1 << 11;        // 16 KB
-            const long long grab = (units > CHUNK ? units : CHUNK) + 8;
+            const long long grab = (units > CHUNK ? ((units + 15) & ~15LL) : CHUNK) + 16;   // whole 128-byte lines (see loci_stride)
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(p.cursor, (unsigned long long) grab);
+            if (lane == 0) base = atomicAdd(p.cursor, (unsigned long long) grab) + (unsigned long long) p.region_begin;
             base = __shfl_sync(FULL, base, 0);
             if ((long long) (base + grab) > p.capacity) {
                 if (lane == 0) atomicAdd(p.cursor, (unsigned long long) (-grab));
@@ -171,10 +181,18 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
         if (lane == 0) w = atomicAdd(p.queue, 1);
         w = __shfl_sync(FULL, w, 0);
         if (w >= p.n_wave) break;
-        if (p.status[w] != ST_DONE) continue;
+        if (p.done_list) {      // ticket w -> the w-th individual the forward kernel finishes
+            if (lane == 0) {
+                const volatile int *slot = p.done_list + w;
+                while ((w = *slot) < 0) __nanosleep(1000);
+                __threadfence();
+            }
+            w = __shfl_sync(FULL, w, 0);
+        }
+        if (__ldcg(p.status + w) != ST_DONE) continue;
         const int row = p.wave[w] - p.first;
-        const LocusRec *rec = p.loci + (size_t) w * (L + 1);
-        const int *lexp = p.locus_exp ? p.locus_exp + (size_t) w * (L + 1) : nullptr;
+        const LocusRec *rec = p.loci + (size_t) w * loci_stride(L);
+        const int *lexp = p.locus_exp ? p.locus_exp + (size_t) w * exp_stride(L) : nullptr;
         const int S_fin = rec[L].count;
         if (S_fin <= 0) {       // unresolvable: HaploBuilder.cpp:117-124
             if (lane == 0) { p.pg[row] = 0.0; p.cov[row] = 0.0; p.nres[row] = 0; p.exp2[row] = 0; }
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32) kbest_kernel(KbParams p)
             if (lane == 0) { p.prior[(size_t) row * K + r] = pr; p.post[(size_t) row * K + r] = post; }
         }
         if (lane == 0) {
-            p.pg[row] = total; p.cov[row] = cov; p.nres[row] = n_sel; p.exp2[row] = p.final_exp[w];
+            p.pg[row] = total; p.cov[row] = cov; p.nres[row] = n_sel; p.exp2[row] = __ldcg(p.final_exp + w);
             for (int r = n_sel; r < K; ++r) { p.prior[(size_t) row * K + r] = 0.0; p.post[(size_t) row * K + r] = 0.0; }
         }
         if (!p.haps) continue;

@@ -24,6 +24,7 @@ EXPORTS = [
     "hmc_resolve_all_device", "hmc_fetch_results", "hmc_estimate_counts", "hmc_estimate_counts_device", "hmc_normalise_counts",
     "hmc_get_counters", "hmc_get_kernel_ms", "hmc_get_trellis", "hmc_mine_patterns", "hmc_fetch_patterns", "hmc_map_patterns", "hmc_mine_patterns_resolved", "hmc_fetch_best_haps", "hmc_result_dims", "hmc_compare", "hmc_set_panel_packed", "hmc_fetch_best_packed",
     "hmc_build_automaton", "hmc_fetch_automaton", "hmc_get_mine_stats", "hmc_result_device_ptrs", "hmc_fetch_counts", "hmc_stream",
+    "hmc_get_likelihood", "hmc_format_best",
 ]
 
 
@@ -70,6 +71,8 @@ def lib():
         L.hmc_fetch_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hmc_stream.restype = C.c_void_p
         L.hmc_stream.argtypes = [C.c_void_p]
+        L.hmc_get_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hmc_format_best.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
@@ -247,6 +250,33 @@ class DeviceBuilder:
             f = out.astype(np.float64)
             return dict(counts=out, switch_error=float(f[0] / f[1]), igp=float(f[2] / f[3]), ihp=float(f[4] / f[5]), bad_individual=bi.value,
                         bad_locus=bl.value)
+
+    def likelihood(self, haps: np.ndarray | None = None) -> np.ndarray:
+        """HaploBuilder::getLikelihood(const Haplotype &) (HaploBuilder.cpp:128-146) of every row of haps [n][L]; None = both haplotypes of
+        the best resolution of every individual of the last resolve call, on the device ([rows][2])."""
+        if haps is None:
+            cnt, k = C.c_int32(), C.c_int32()
+            self._ck(lib().hmc_result_dims(self._h, C.byref(cnt), C.byref(k)))
+            out = np.zeros((cnt.value, 2))
+            self._ck(lib().hmc_get_likelihood(self._h, 2 * cnt.value, None, _p(out)))
+            return out
+        haps = np.ascontiguousarray(haps, np.int8)
+        out = np.zeros(haps.shape[:-1])
+        self._ck(lib().hmc_get_likelihood(self._h, int(out.size), _p(haps), _p(out)))
+        return out
+
+    def format_best(self, symbols: np.ndarray, allele_type: str):
+        """The allele lines of `.reconstructed` for the last resolve call, formatted on the device (HaploFile.cpp:146-148): returns
+        (text bytes, line offsets [2 * rows + 1])."""
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        cnt, k = C.c_int32(), C.c_int32()
+        self._ck(lib().hmc_result_dims(self._h, C.byref(cnt), C.byref(k)))
+        off = np.zeros(2 * cnt.value + 1, np.int64)
+        total = C.c_int64()
+        self._ck(lib().hmc_format_best(self._h, _p(symbols), allele_type.encode(), None, 0, _p(off), C.byref(total)))
+        buf = np.zeros(total.value, np.uint8)
+        self._ck(lib().hmc_format_best(self._h, _p(symbols), allele_type.encode(), _p(buf), total.value, _p(off), C.byref(total)))
+        return buf.tobytes(), off
 
     def mine_stats(self) -> dict:
         ms, nodes, levels, mx, sw, wr = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

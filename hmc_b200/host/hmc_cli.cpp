@@ -121,7 +121,7 @@ int main(int argc, char **argv)
             printf("Solving Time = %f (mining %.3f s, device %.3f s, host M-step %.3f s)\n", hm.seconds[0] + hm.seconds[1] + hm.seconds[2], hm.seconds[0], hm.seconds[1], hm.seconds[2]);
         }
         if (HaploFile::isBinary(input)) HaploFile::writeBinary(input + ".reconstructed", genos, resolutions);     // output in the input's format
-        else file.writeGenoData(genos, resolutions, ".reconstructed");
+        else hm.writeReconstructed(file, genos, resolutions, ".reconstructed");
         return 0;
     }
     catch (const std::exception &e) {

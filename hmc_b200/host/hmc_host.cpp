@@ -304,6 +304,23 @@ void HaploFile::writeGenoData(const GenoData &genos, const std::vector<int8_t> &
     fclose(fp);
 }
 
+void HaploFile::writeGenoText(const GenoData &genos, const char *text, const int64_t *line_off, const char *suffix) const
+{
+    const std::string out = m_filename + suffix;
+    FILE *fp = fopen(out.c_str(), "w");
+    if (!fp) throw HmcError("Can not open file " + out + "!");
+    fprintf(fp, "%d\n%d\nP", genos.N, genos.L);
+    for (int i = 0; i < genos.L; ++i) fprintf(fp, " %d", genos.position[i]);
+    fprintf(fp, "\n%s\n", genos.allele_type.c_str());
+    for (int i = 0; i < genos.N; ++i) {
+        const std::string &id = genos.ids[i];
+        if (!id.empty() && id[0] >= '0' && id[0] <= '9') fprintf(fp, "#%s\n", id.c_str());
+        else fprintf(fp, "%s\n", id.c_str());
+        fwrite(text + line_off[2 * i], 1, (size_t) (line_off[2 * i + 2] - line_off[2 * i]), fp);      // both lines, newlines included
+    }
+    fclose(fp);
+}
+
 // ---------------------------------------------------------------------------------------------
 int PatternSet::add(int start, const int8_t *a, int len, double f, double pf, double tp)
 {
@@ -1042,6 +1059,7 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
     const int N = g.N, L = g.L;
     ResolveResult r;
     double t0 = now_s();
+    m_device_rows_current = false;
     // One GPU holds every individual and the next search runs on it: the K sampled pairs stay on the device and are named by
     // their result rows (hmc_mine_patterns_resolved); only the best pair of every individual comes back.
     // (sharded runs with a device-side all-gather hold every individual's rows on every rank too)
@@ -1085,6 +1103,25 @@ double HaploModel::resolveAll(std::vector<int8_t> &resolved)
     for (double w : m_samples.w) m_samples.total_weight += w;      // HaploData::checkTotalWeight
     seconds[2] += now_s() - t0;
     return r.ll;
+}
+
+bool HaploModel::writeReconstructed(const HaploFile &file, const GenoData &genos, const std::vector<int8_t> &res, const char *suffix)
+{
+    int32_t rows = 0, K = 0;
+    if (getenv("HMC_B200_HOST_FORMAT") || !m_device_rows_current || hmc_result_dims(m_ctx, &rows, &K) != HMC_OK || rows != genos.N) {
+        file.writeGenoData(genos, res, suffix);
+        return false;
+    }
+    const int L = genos.L, A = genos.Amax;
+    std::vector<int32_t> sym((size_t) L * A, 0);
+    for (int l = 0; l < L; ++l) for (size_t k = 0; k < genos.symbols[l].size() && (int) k < A; ++k) sym[(size_t) l * A + k] = genos.symbols[l][k];
+    std::vector<int64_t> off((size_t) 2 * rows + 1);
+    int64_t total = 0;
+    ck(m_ctx, hmc_format_best(m_ctx, sym.data(), genos.allele_type.c_str(), nullptr, 0, nullptr, &total), "hmc_format_best");
+    std::vector<char> text((size_t) total);
+    ck(m_ctx, hmc_format_best(m_ctx, sym.data(), genos.allele_type.c_str(), text.data(), total, off.data(), &total), "hmc_format_best");
+    file.writeGenoText(genos, text.data(), off.data(), suffix);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1131,6 +1168,7 @@ void HaploModel::run(const GenoData &genos, std::vector<int8_t> &resolutions)
         const double ll = resolveAll(resolved);
         ll_trace.push_back(ll);
         if (ll >= old_ll) resolutions = resolved;
+        m_device_rows_current = ll >= old_ll;          // the rows on the device are the resolutions just adopted (or a worse pass that was not)
         if (verbose) {      // HaploModel.cpp:134-137
             HaploComp compare(*this, m_unphased.N, m_unphased.L, m_unphased.idx.data(), resolutions.data());
             fprintf(stderr, "  iteration %d: patterns %d, Switch Error = %f, IHP = %f, IGP = %f, LL = %f\n", iter, m_patterns.size(), compare.switch_error(),

@@ -60,6 +60,8 @@ public:
     static void writeBinary(const std::string &path, const GenoData &genos, const std::vector<int8_t> &idx);
     // writes allele INDICES `res` ([N][2][L], mapped back through the symbol table) to filename + suffix
     void writeGenoData(const GenoData &genos, const std::vector<int8_t> &res, const char *suffix = "") const;
+    // the same file from allele lines that arrive formatted (hmc_format_best): line 2 * i + h of `text` is haplotype h of individual i
+    void writeGenoText(const GenoData &genos, const char *text, const int64_t *line_off, const char *suffix = "") const;
 };
 
 // HaploPattern (HaploPattern.h:19-24) as a plain record; alleles live in the manager's pool.
@@ -250,6 +252,11 @@ public:
     void setCliDefaults();      // HMC.cpp:35-47
     // HaploModel::run (HaploModel.cpp:117-155); resolutions: [N][2][L] allele indices
     void run(const GenoData &genos, std::vector<int8_t> &resolutions);
+    // `.reconstructed` (HMC.cpp:228): the allele lines are formatted on the device when it holds the best resolution of every
+    // individual (K8b, hmc_format_best); `res` (what run() returned) is written through the host formatter otherwise.  Returns
+    // true when the device formatted the text.
+    bool m_device_rows_current = false;     // the best rows of the last device resolve are what run() returned
+    bool writeReconstructed(const HaploFile &file, const GenoData &genos, const std::vector<int8_t> &res, const char *suffix = ".reconstructed");
     GenoData &working() { return m_unphased; }
     void build(GenoData &genos);
     void findPatterns();

@@ -137,7 +137,7 @@ int hmch_set_device_collectives(void *p, hmch_reduce_dev_fn reduce, hmch_gather_
 int hmch_write_reconstructed(void *p, const char *path, const char *suffix)
 {
     Handle *h = (Handle *) p;
-    GUARD(HaploFile(path).writeGenoData(h->input, h->resolutions, suffix));
+    GUARD(h->hm->writeReconstructed(HaploFile(path), h->input, h->resolutions, suffix));
 }
 
 }  // extern "C"

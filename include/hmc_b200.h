@@ -193,6 +193,22 @@ int hmc_get_mine_stats(hmc_ctx *ctx, double *ms, int64_t *nodes, int64_t *levels
  * %d!", Genotype.cpp:258-261,272-275) returns HMC_ERR_INVALID with the first offending individual / locus. */
 int hmc_compare(hmc_ctx *ctx, int N, int L, const int8_t *real, const int8_t *infer, int64_t out[6], int32_t *bad_individual, int32_t *bad_locus);
 
+/* K8a: HaploBuilder::getLikelihood(const Haplotype &) (HaploBuilder.cpp:128-146; the Genotype overload :148-151 is the product of the
+ * two haplotypes' values): likelihood of n fully typed haplotypes [n][L] (allele indices) under the model on the device -- the product
+ * of the transition probabilities of the longest matching pattern ending at every index head_len .. L, 0 when no pattern matches.
+ * haps == NULL takes both haplotypes of the best resolution of every individual of the last resolve call where they lie on the
+ * device (n = 2 * result rows).  A missing or out-of-range allele returns HMC_ERR_INVALID. */
+int hmc_get_likelihood(hmc_ctx *ctx, int n, const int8_t *haps, double *out);
+
+/* K8b: the allele lines of `.reconstructed` (HaploFile::writeGenoData, HaploFile.cpp:146-148 through AlleleSequence::write /
+ * writeAllele, Allele.cpp:82-101) formatted on the device from the best resolution of every individual of the last resolve call
+ * (the input genotype for an individual that could not be resolved, HaploBuilder.cpp:117-124).  symbols [L][Amax]: the value of
+ * every allele index -- the character at an 'S' locus, the integer at any other; allele_type [L].  Two lines per result row, each
+ * ending in '\n'; line_off [2 * rows + 1] (may be NULL) receives the byte offset of every line, *total the size of the text.
+ * out == NULL only sizes; a buffer smaller than the text returns HMC_ERR_LIMIT with *total set. */
+int hmc_format_best(hmc_ctx *ctx, const int32_t *symbols, const char *allele_type, char *out, int64_t capacity, int64_t *line_off,
+                    int64_t *total);
+
 /* Structural counters of the last resolve/estimate call (HMC_CNT_*), for parity and the roofline. */
 int hmc_get_counters(hmc_ctx *ctx, int64_t out[HMC_CNT_N]);
 /* Device time (ms, CUDA events) of the kernels of the last call: [0] forward, [1] traceback, [2] backward, [3] E-step. */

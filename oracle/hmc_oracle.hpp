@@ -401,6 +401,18 @@ struct Builder {
 
     int lastA(int id) const { return model->pats[id].al.back(); }
 
+    // HaploBuilder.cpp:128-146 (dead in the reference: its only callers are commented out, HMC.cpp:222-223): one trie descent per index
+    double getLikelihood(const int8_t *hap) const
+    {
+        double likelihood = 1.0;
+        for (int i = model->head_len(); i <= panel->L; ++i) {
+            const int hp = model->trie.findLongestMatch(i, hap, panel->L, 0, model->pats, panel->nall);
+            if (hp >= 0) likelihood *= model->pats[hp].tp;
+            else { likelihood = 0; break; }
+        }
+        return likelihood;
+    }
+
     // HaploBuilder.cpp:153-224 + HaploPair head ctor HaploPair.cpp:14-33
     void initHeadList(int gi)
     {

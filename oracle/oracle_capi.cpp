@@ -105,6 +105,12 @@ void orc_counters(void *p, long long *out4)
     Counters &c = ((Handle *) p)->hm.builder.cnt;
     out4[0] = c.steps; out4[1] = c.states; out4[2] = c.max_states; out4[3] = c.arrivals;
 }
+// HaploBuilder::getLikelihood(const Haplotype &) of n haplotypes [n][L]
+void orc_get_likelihood(void *p, int n, const int8_t *haps, double *out)
+{
+    Handle *h = (Handle *) p;
+    for (int q = 0; q < n; ++q) out[q] = h->hm.builder.getLikelihood(haps + (size_t) q * h->hm.panel.L);
+}
 int orc_num_res(void *p, int i) { return (int) ((Handle *) p)->hm.klists[i].size(); }
 // K-list of individual i after orc_resolve_all: priors/posteriors [n], haps [n][2][L]; returns P(G) (scaled) and exponent
 void orc_get_individual(void *p, int i, double *pg, int *exp2, double *prior, double *post, int8_t *haps)

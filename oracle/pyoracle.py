@@ -123,6 +123,13 @@ class Oracle:
         lib().orc_get_individual(self._h, i, C.byref(pg), C.byref(ex), _p(prior), _p(post), _p(haps))
         return dict(pg=pg.value, exp=ex.value, n=n, prior=prior[:n], posterior=post[:n], haps=haps[:n])
 
+    def likelihood(self, haps: np.ndarray) -> np.ndarray:
+        """HaploBuilder::getLikelihood(const Haplotype &) (HaploBuilder.cpp:128-146) of every row of haps [n][L]."""
+        haps = np.ascontiguousarray(haps, np.int8).reshape(-1, self.L)
+        out = np.zeros(len(haps))
+        lib().orc_get_likelihood(self._h, C.c_int(len(haps)), _p(haps), _p(out))
+        return out
+
     def resolution(self, i: int) -> np.ndarray:
         h = np.zeros((2, self.L), np.int8)
         lib().orc_get_resolution(self._h, i, _p(h))
