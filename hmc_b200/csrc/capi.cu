@@ -363,9 +363,9 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     if (rc) return rc;
     CK(ctx->d_cursor.ensure(2));         // [0] forward (and serial K-best), [1] streamed K-best
     CK(ctx->d_flags.ensure(4));          // [0] arena exhausted, [1] forward queue, [2] K-best queue, [3] done count
-    CK(ctx->d_counters.ensure(32));
+    CK(ctx->d_counters.ensure(72));
     ctx->ecache.valid = false;
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 72 * sizeof(long long), ctx->stream));
     memset(ctx->counters, 0, sizeof ctx->counters);
     memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
 
@@ -534,13 +534,22 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         pending.erase(pending.begin(), pending.begin() + n_wave);
         pending.insert(pending.begin(), again.begin(), again.end());
     }
-    long long hc[32];
+    long long hc[72];
     CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ctx->h_work.data(), ctx->d_work.p, sizeof(long long) * ctx->N, cudaMemcpyDeviceToHost));
     if (getenv("HMC_B200_PRINT_PASSES"))
         for (int b = 8; b < 24; b += 8)
             fprintf(stderr, "%s pass Mcycles: [0] %lld  [1] %lld  [2] %lld  [3] %lld  [4] %lld  [5] %lld  [7] %lld | [6] %lld\n", b == 8 ? "fast " : "spill",
                     hc[b] >> 20, hc[b + 1] >> 20, hc[b + 2] >> 20, hc[b + 3] >> 20, hc[b + 4] >> 20, hc[b + 5] >> 20, hc[b + 7] >> 20, hc[b + 6]);
+#ifdef HMC_PROFILE_PASSES
+    if (getenv("HMC_B200_PRINT_PASSES")) {
+        long long tc = 0, tn = 0;
+        for (int b = 0; b < 18; ++b) { tc += hc[32 + b]; tn += hc[50 + b]; }
+        for (int b = 0; b < 18; ++b)
+            if (hc[50 + b]) fprintf(stderr, "steps with < %6d candidates: %5.1f %% of the steps, %5.1f %% of the step cycles, %7.0f cycles per step\n", 1 << b, 100.0 * hc[50 + b] / tn,
+                                    100.0 * hc[32 + b] / tc, (double) hc[32 + b] / hc[50 + b]);
+    }
+#endif
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;

@@ -40,6 +40,12 @@
 // sub-partition holds at 3 CTAs per SM leave 1,024 registers at the 80 ptxas picks on its own (room for a 32-register warp: measured with a
 // probe kernel) and 2,560 at 72, which is one streamed K-best warp at 80 registers beside them.  The cap costs the forward kernel 4 bytes
 // more spill and 1.4 ms on C2; 64 / 64 (two K-best warps per sub-partition) costs it 7 ms.
+#ifndef FWD_SMEM_META
+#define FWD_SMEM_META 1
+#endif
+#ifndef FWD_SMEM_TPV
+#define FWD_SMEM_TPV 0
+#endif
 #ifndef FWD_MAXNREG
 #define FWD_MAXNREG 72
 #endif
@@ -91,9 +97,13 @@ struct FwdSmem {
     // compare-and-swap is the one access of the step a warp has to wait for slot by slot (probe chains), and on the L2-resident spill
     // hash it was a third of all warp time; the other slot fields of such a step live in the global scratch (reductions / later passes).
     static constexpr int KB = FWD_SMEM_KEYS;
+    // ... and in the shipped 256-thread configuration (3 CTAs per SM, 65 KB each) so do the three 32-bit slot fields the later passes
+    // update with atomics (smallest ordinal, arrival count, segment offset); the tp product of the slot is written once and read once and stays global
+    static constexpr int MB = (FWD_SMEM_META && NT >= 256 && KB > HC) ? KB : HC;
+    static constexpr int TB = FWD_SMEM_TPV ? MB : HC;
     u64 keys[KB > HC ? KB : HC];
-    double tpv[HC];
-    u32 ord[HC], cnt[HC], soff[HC];
+    double tpv[TB];
+    u32 ord[MB], cnt[MB], soff[MB];
     double alpha[2][CC], v1[2][CC];
     long long ll[4];                // -, alloc result, chunk cursor, chunk end
     unsigned long long look[8];     // look-back ring of pass C: tag << 48 | creators << 24 | arrivals (inclusive prefix of a tile)
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
     const int4 *const succ16 = reinterpret_cast<const int4 *>(md.succ16);
 
     if (tid == 0) { sm.ll[2] = 0; sm.ll[3] = 0; }
-    for (int h = tid; h < Smem::HC; h += NT) { sm.ord[h] = 0xFFFFFFFFu; sm.cnt[h] = 0; }
+    for (int h = tid; h < Smem::MB; h += NT) { sm.ord[h] = 0xFFFFFFFFu; sm.cnt[h] = 0; }
     for (int h = tid; h < (Smem::KB > Smem::HC ? Smem::KB : Smem::HC); h += NT) sm.keys[h] = KEY_EMPTY;
 
     // chunked bump allocation (thread 0 only); returns -1 when the arena is exhausted
@@ -257,6 +267,9 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
         long long pass_cyc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool pass_fast = true;
         long long t_mark = clock64();
+        long long hist_cyc[18], hist_n[18], t_step = 0;     // steps by candidate count: bucket b holds C in [2^(b-1), 2^b)
+        for (int q = 0; q < 18; ++q) { hist_cyc[q] = 0; hist_n[q] = 0; }
+        int hist_b = 0;
 #endif
         par = 0;
         long long c_steps = 0, c_states = S_in, c_max = S_in, c_arr = 0, c_spill = 0;
@@ -316,6 +329,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
 #ifdef HMC_PROFILE_PASSES
             pass_fast = fast;
             if (tid == 0) { if (fast) pass_cyc[6] += C; else pass_cyc[14] += C; }
+            hist_b = min(17, 32 - __clz(max(C, 1))); t_step = clock64();
 #endif
 
             int S_out = 0, new_exp = cur_exp;
@@ -323,8 +337,9 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
             int rc = 0;         // 0 = ok, 1 = every extension died, 2 = status set (the hash arrays were reset)
             do {
                 HashTab tab;
-                tab.keys = (fast || hsize <= Smem::KB) ? sm.keys : sc.keys; tab.tpvs = fast ? sm.tpv : sc.tpv; tab.ord = fast ? sm.ord : sc.ord;
-                tab.cnt = fast ? sm.cnt : sc.cnt; tab.soffs = fast ? sm.soff : sc.soff;
+                tab.keys = (fast || hsize <= Smem::KB) ? sm.keys : sc.keys; tab.tpvs = (fast || hsize <= Smem::TB) ? sm.tpv : sc.tpv;
+                const bool meta_sm = fast || hsize <= Smem::MB;
+                tab.ord = meta_sm ? sm.ord : sc.ord; tab.cnt = meta_sm ? sm.cnt : sc.cnt; tab.soffs = meta_sm ? sm.soff : sc.soff;
                 int *const cand = fast ? sm.cand : sc.cand;
                 int *const sarr = fast ? sm.sarr : sc.sarr;
                 int2 *const mlist = fast ? sm.mlist : sc.mlist;
@@ -469,15 +484,23 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 {
                     const int ntiles = (C + 31) >> 5;
                     const u32 lt_mask = (1u << lane) - 1u;
+                    int enc_nx = (wid < ntiles && (wid << 5) + lane < C) ? cand[(wid << 5) + lane] : -1;
 #pragma unroll 1
                     for (int tile = wid; tile < ntiles; tile += NW) {
                         const int c = (tile << 5) + lane;
-                        const int enc = (c < C) ? cand[c] : -1;
+                        const int enc = enc_nx;
+                        { const int c2 = c + (NW << 5); enc_nx = (c2 < C) ? cand[c2] : -1; }      // the next tile's slots, one trip ahead
                         const u32 h = (u32) enc & SLOT_MASK;
                         u32 so = 0xFFFFFFFFu, sn = 0;
                         u64 key = 0;
-                        double tv = 0.0;
-                        if (enc >= 0) { so = tab.ord[h]; sn = tab.cnt[h]; key = tab.keys[h]; tv = tab.tpvs[h]; }       // four loads, one trip
+                        double tv = 0.0, pa = 0.0, pv = 0.0;
+                        int g = 0, s = 0, dir = 0;
+                        if (enc >= 0) {     // the slot's four fields and the predecessor's alpha / v1 (used if this turns out a single-arrival creator): one trip
+                            so = tab.ord[h]; sn = tab.cnt[h]; key = tab.keys[h]; tv = tab.tpvs[h];
+                            decode(c, g, s, dir);
+                            pa = in_alpha[s];
+                            if (!estep) pv = in_v1[s];
+                        }
                         const bool cr = enc >= 0 && so == (u32) c;
                         const int nn = cr ? (int) sn : 0;
                         const u32 crm = __ballot_sync(FULL, cr);
@@ -501,8 +524,6 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         const int idx = (int) ((prevp >> 24) & 0xFFFFFFull) + __popc(crm & lt_mask);
                         const int off = (int) (prevp & 0xFFFFFFull) + xa - nn;
                         const u32 rev = ((u32) enc >> 30) & 1u;
-                        int g, s, dir;
-                        decode(c, g, s, dir);
                         const int gxv = sm.gx[g], gyv = sm.gy[g];
                         const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
                         const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
@@ -516,12 +537,12 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(succ16 + (size_t) hpb * A));
 #endif
                         if (nn == 1) {
-                            const double alpha = __dmul_rn(in_alpha[s], tv);
+                            const double alpha = __dmul_rn(pa, tv);
                             ST_OUT(t_alpha + idx, alpha);
                             if (out_cache) co_alpha[idx] = alpha;
                             amax = fmax(amax, alpha);
                             if (!estep) {
-                                const double v = __dmul_rn(in_v1[s], tv);
+                                const double v = __dmul_rn(pv, tv);
                                 ST_OUT(t_v1 + idx, v);
                                 if (out_cache) co_v1[idx] = v;
                                 ST_OUT(t_arr + off, (u32) s | (gxv != gyv ? ARR_HET : 0u) | (rev ? ARR_REV : 0u));
@@ -703,6 +724,9 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
             S_in = S_out; par ^= 1; cur_off = new_off;
             block_sync<NT>();
             PASS_MARK(5);
+#ifdef HMC_PROFILE_PASSES
+            hist_cyc[hist_b] += clock64() - t_step; ++hist_n[hist_b];
+#endif
         }
         block_sync<NT>();
         if (tid == 0) {
@@ -722,6 +746,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 atomicAdd((unsigned long long *) p.counters + 5, (unsigned long long) c_spill);
 #ifdef HMC_PROFILE_PASSES
                 for (int q = 0; q < 16; ++q) atomicAdd((unsigned long long *) p.counters + 8 + q, (unsigned long long) pass_cyc[q]);
+                for (int q = 0; q < 18; ++q) { atomicAdd((unsigned long long *) p.counters + 32 + q, (unsigned long long) hist_cyc[q]); atomicAdd((unsigned long long *) p.counters + 50 + q, (unsigned long long) hist_n[q]); }
 #endif
             }
             publish(w);

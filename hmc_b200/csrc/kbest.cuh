@@ -379,44 +379,55 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
             return ref;
         };
         // appends one more link to the list of node `top` (or marks it exhausted); nodes below it are advanced as needed.
-        // Per visit the node is read once with the lanes spread over its streams (lane e holds head / arrival word / predecessor node /
-        // next index of stream e), the header by broadcast; updates go back as single stores, nothing is re-read.
+        // The chain of visits is a chain of dependent L2 round trips, so a visit is kept to two: (1) the 32-byte header and, with the lanes
+        // spread over the streams (lane e holds head / arrival word / predecessor node / next index of stream e), the stream arrays -- issued
+        // together, lanes past nS read inside the node and are masked afterwards; (2) the predecessor's header and the link the pending
+        // stream wants.  A visit that comes back UP from a predecessor it had to advance takes that link from registers instead of (2).
+        // Updates go back as single stores, nothing is re-read.
         auto lazy_next = [&](u32 top) {
             int sp = 0;
             u32 cur = top;
+            bool up = false;            // the previous visit was of the pending stream's predecessor, which ...
+            double up_v = -1.0;         // ... appended this link (< 0: it ran dry instead)
             for (;;) {
                 __syncwarp();
                 KbNode nd = node_at(cur);
                 const uint4 hdr = *reinterpret_cast<const uint4 *>(nd.b);           // level, state, next, {nD, nS, pending, exhausted}
-                const int ns = (int) ((hdr.w >> 8) & 0xFFu), pend = (int) ((hdr.w >> 16) & 0xFFu);
-                int k = (int) (hdr.w & 0xFFu);
+                const double2 tf = *reinterpret_cast<const double2 *>(nd.b + 16);   // tpv, fac
                 double my_head = -1.0;
                 u32 my_sw = 0, my_sn = 0;
                 int my_j = 0;
-                if (lane < ns) { my_head = nd.head()[lane]; my_sw = nd.sword()[lane]; my_sn = nd.snode()[lane]; my_j = nd.sj()[lane]; }
+                if (lane < K) { my_head = nd.head()[lane]; my_sw = nd.sword()[lane]; my_sn = nd.snode()[lane]; my_j = nd.sj()[lane]; }
+                const int ns = (int) ((hdr.w >> 8) & 0xFFu), pend = (int) ((hdr.w >> 16) & 0xFFu);
+                const int k = (int) (hdr.w & 0xFFu);
+                if (lane >= ns) { my_head = -1.0; my_sw = 0; my_sn = 0; my_j = 0; }
                 if (pend != (int) KB_NONE) {
                     const int j = __shfl_sync(FULL, my_j, pend);
                     double hv = -1.0;
                     if (j < K) {
-                        u32 pref = __shfl_sync(FULL, my_sn, pend);
-                        if (!pref) {
-                            pref = find_or_create((int) hdr.x - 1, (int) (__shfl_sync(FULL, my_sw, pend) & ARR_PRED_MASK));
-                            if (!pref) return;
-                            if (lane == pend) { my_sn = pref; nd.snode()[pend] = pref; }
+                        double pv = -1.0;
+                        if (up) pv = up_v;      // the predecessor's list grew to index j a moment ago (it was at j: lists grow on demand only)
+                        else {
+                            u32 pref = __shfl_sync(FULL, my_sn, pend);
+                            if (!pref) {
+                                pref = find_or_create((int) hdr.x - 1, (int) (__shfl_sync(FULL, my_sw, pend) & ARR_PRED_MASK));
+                                if (!pref) return;
+                                if (lane == pend) { my_sn = pref; nd.snode()[pend] = pref; }
+                            }
+                            KbNode pd = node_at(pref);
+                            const u32 pw = *reinterpret_cast<const u32 *>(pd.b + 12);
+                            const double pj = pd.dv()[j];           // (read before it is known to be valid: inside the node)
+                            if ((int) (pw & 0xFFu) > j) pv = pj;
+                            else if (!(pw >> 24)) {     // the predecessor's list has to grow first
+                                if (lane == 0) stack[sp] = cur;
+                                ++sp;
+                                cur = pref;
+                                continue;
+                            }
                         }
-                        KbNode pd = node_at(pref);
-                        const u32 pw = *reinterpret_cast<const u32 *>(pd.b + 12);
-                        const double pv = pd.dv()[j];           // (read before it is known to be valid: inside the node)
-                        if ((int) (pw & 0xFFu) > j) {
-                            hv = __dmul_rn(pv, nd.tpv());
-                            const double fac = nd.fac();
-                            if (fac != 1.0) hv *= fac;
-                        }
-                        else if (!(pw >> 24)) {     // the predecessor's list has to grow first
-                            if (lane == 0) stack[sp] = cur;
-                            ++sp;
-                            cur = pref;
-                            continue;
+                        if (pv >= 0.0) {
+                            hv = __dmul_rn(pv, tf.x);
+                            if (tf.y != 1.0) hv *= tf.y;
                         }
                     }
                     if (lane == pend) { my_head = hv; nd.head()[pend] = hv; }
@@ -443,6 +454,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
                 ++n_next;
                 if (sp == 0) break;
                 --sp;
+                up = true; up_v = bv;       // (bv < 0: nothing was appended)
                 __syncwarp();
                 cur = stack[sp];
             }
