@@ -34,18 +34,23 @@
 #include <type_traits>
 
 #ifndef FWD_SMEM_KEYS
-#define FWD_SMEM_KEYS 2048
+#define FWD_SMEM_KEYS 2048      // hash slots whose keys (and, see FwdSmem, 32-bit fields) live in shared memory
+#endif
+#ifndef FWD_SMEM_META
+#define FWD_SMEM_META 1
+#endif
+#ifndef FWD_SMEM_TPV
+#define FWD_SMEM_TPV 0          // the slot's tp product too: 75 KB per CTA, the carve-out leaves 28 KB of L1 -- 111 vs 91 ms
+#endif
+// The successor rows a new state will gather in the next step are prefetched when pass C creates it: into L1 (and read through it) now that the
+// hash of mid-size steps no longer competes for it -- 1.8 ms on C2 against the L2-only prefetch + ld.cg.
+#ifndef FWD_PREFETCH_L1
+#define FWD_PREFETCH_L1 1
 #endif
 // Register cap of the shipped 256-thread configuration.  Registers are allocated per SM sub-partition (16,384 each): the 6 forward warps a
 // sub-partition holds at 3 CTAs per SM leave 1,024 registers at the 80 ptxas picks on its own (room for a 32-register warp: measured with a
 // probe kernel) and 2,560 at 72, which is one streamed K-best warp at 80 registers beside them.  The cap costs the forward kernel 4 bytes
 // more spill and 1.4 ms on C2; 64 / 64 (two K-best warps per sub-partition) costs it 7 ms.
-#ifndef FWD_SMEM_META
-#define FWD_SMEM_META 1
-#endif
-#ifndef FWD_SMEM_TPV
-#define FWD_SMEM_TPV 0
-#endif
 #ifndef FWD_MAXNREG
 #define FWD_MAXNREG 72
 #endif
@@ -400,9 +405,14 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                             const int nd = het ? 2 : 1;
                             int4 ea[2], eb[2];
                             ea[0] = ea[1] = eb[0] = eb[1] = make_int4(-1, 0, 0, 0);
-                            if (alive) {        // L2 only: the successor table would only evict the hash / segment arrays from L1
+                            if (alive) {        // (prefetched by the pass C that created the state)
+#if FWD_PREFETCH_L1
+                                ea[0] = ra[x]; eb[0] = rb[y];
+                                if (het) { ea[1] = ra[y]; eb[1] = rb[x]; }
+#else
                                 ea[0] = __ldcg(ra + x); eb[0] = __ldcg(rb + y);
                                 if (het) { ea[1] = __ldcg(ra + y); eb[1] = __ldcg(rb + x); }
+#endif
                             }
                             // both orientations: keys first, then the two compare-and-swaps in flight together
                             u64 key[2];
@@ -533,8 +543,13 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         if (out_cache) { co_ida[idx] = hpa; co_idb[idx] = hpb; }
 #ifndef FWD_NO_PREFETCH
                         // the next step gathers the successor rows of this state: start moving them to L2 now (a row of a biallelic model is one sector)
+#if FWD_PREFETCH_L1
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(succ16 + (size_t) hpa * A));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(succ16 + (size_t) hpb * A));
+#else
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(succ16 + (size_t) hpa * A));
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(succ16 + (size_t) hpb * A));
+#endif
 #endif
                         if (nn == 1) {
                             const double alpha = __dmul_rn(pa, tv);
@@ -602,6 +617,8 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         cx(3, 4);
                     }
                     else cx(0, 1);
+                    // (fetching all predecessors' alpha / v1 in one trip before the ordered sum, or one arrival ahead, was measured: 1 ms SLOWER -- the
+                    // kernel is bound by the instructions a warp issues per step more than by these trips)
                     double alpha = 0.0, vmax = 0.0;
 #pragma unroll 1
                     for (int q = 0; q < n; ++q) {

@@ -1,6 +1,7 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-make -C oracle -s
-timeout 900 python -m pytest tests/test_gpu_forward.py tests/test_gpu_edge.py tests/test_gpu_estep.py -x -q 2>&1 | tail -3
-echo "--- shipped streamed"; timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | tail -1
-echo "--- shipped serial"; HMC_B200_KBEST_SERIAL=1 timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | tail -1
+export REPS=7
+for v in "" e2 "" e2; do
+  if [ -n "$v" ]; then export HMC_B200_LIB=$PWD/build/var/libhmc_$v.so; else unset HMC_B200_LIB; fi
+  echo "--- ${v:-pfl1}"; timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | tail -1
+done
