@@ -376,8 +376,11 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 }
                 int *fwd = (int *) (arena + fwd_off);
 
+                // (a typed locus is one group: the ordinal is the state, or state * 2 + orientation at a heterozygous one)
+                const bool one_group = ng == 1, het0 = sm.gx[0] != sm.gy[0];
                 auto decode = [&](int c, int &g, int &s, int &dir) {
                     g = 0;
+                    if (one_group) { s = het0 ? c >> 1 : c; dir = het0 ? (c & 1) : 0; return; }
 #pragma unroll 1
                     while (g + 1 < ng && c >= sm.gbase[g + 1]) ++g;
                     const int r = c - sm.gbase[g];
