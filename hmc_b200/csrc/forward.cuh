@@ -111,14 +111,15 @@ struct FwdSmem {
     u32 ord[MB], cnt[MB], soff[MB];
     double alpha[2][CC], v1[2][CC];
     long long ll[4];                // -, alloc result, chunk cursor, chunk end
-    unsigned long long look[8];     // look-back ring of pass C: tag << 48 | creators << 24 | arrivals (inclusive prefix of a tile)
+    unsigned long long look[2][8];  // look-back ring of pass C: tag << 48 | creators << 24 | arrivals (inclusive prefix of a tile); by step parity
+    int cnts[2][4];                 // new states, arrivals, states with 2..8 / more arrivals of the step; by step parity (the other set is zeroed during a step)
     double red[NT / 32 + 1];
     alignas(16) int cand[CC];
     int sarr[CC];
     int2 mlist[CC / 2 + 1];
     int ida[2][CC], idb[2][CC];
     int gx[MAX_GROUPS], gy[MAX_GROUPS], gbase[MAX_GROUPS + 1];
-    int ints[8];                    // 0 queue ticket, 1 head count, 2 status, 3 arena exhausted, 4 new states, 5 arrivals, 6 / 7 states with 2..4 / more arrivals
+    int ints[8];                    // 0 queue ticket, 1 head count, 2 status, 3 arena exhausted
 };
 
 template <int NT, int CC, int MINB, bool ESTEP>
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
         const u32 gmask = (1u << gbits) - 1u;
         auto geno_word = [&](int l) -> u32 { const int bit = l * 2 * gbits; return gp[bit >> 5] >> (bit & 31); };
 
+        if (tid < 16) (&sm.look[0][0])[tid] = 0;
+        if (tid < 8) (&sm.cnts[0][0])[tid] = 0;
         // ---------------- head states (initHeadList), serial: at most A^head_len pairs ----------------
         int S_in = 0, par = 0, status = ST_DONE, cur_exp = 0;
         long long cur_off = 0;
@@ -297,11 +300,10 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
             if (i + 1 < L) { nx_word = geno_word(i + 1); nx_info = pn.linfo[i + 1]; }
             // allele-pair groups in the reference's extendAll order (HaploBuilder.cpp:48-79): one group at a typed locus; at a locus with
             // missing alleles thread 0 lists them
+            // (a typed locus -- 95 % of the steps -- keeps its one group in registers: no shared-memory traffic and no barrier for it)
             int ng = 1, C = S_in * (g0 != g1 ? 2 : 1);
-            if (g0 >= 0 && g1 >= 0) {
-                if (tid == 0) { sm.gx[0] = g0; sm.gy[0] = g1; sm.gbase[0] = 0; sm.gbase[1] = C; }
-            }
-            else {
+            const bool typed = g0 >= 0 && g1 >= 0;
+            if (!typed) {
                 if (tid == 0) {
                     int n = 0, c = 0;
                     auto add_group = [&](int x, int y) { sm.gx[n] = x; sm.gy[n] = y; sm.gbase[n] = c; c += S_in * (x != y ? 2 : 1); ++n; };
@@ -323,8 +325,9 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 block_sync<NT>();
                 ng = sm.ints[1]; C = sm.gbase[ng];
             }
-            if (tid == 0) { sm.ints[4] = 0; sm.ints[5] = 0; sm.ints[6] = 0; sm.ints[7] = 0; }
-            if (tid < 8) sm.look[tid] = 0;
+            // step counters and look-back ring of this step (zeroed during the previous one: no barrier needed before they are used)
+            int *const cn = sm.cnts[par];
+            unsigned long long *const lk = sm.look[par];
             // hash size: 1.3 C slots (load <= 0.77 even if every candidate were a new state, ~0.45 typically), NOT rounded to a power of
             // two: the slots a step touches lie 2-3x denser, and the spill hash of all resident CTAs has to live in L2 between passes
             const int hsize = ((C + C / 4 + C / 16 + 63) >> 6) << 6;
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 // forward-link block of index i (E-step mode)
                 long long fwd_off = 0;
                 if (estep && tid == 0) sm.ll[1] = alloc(((long long) C + 1) / 2);
-                block_sync<NT>();       // groups / counters / look-back ring visible, fwd allocation visible
+                if (estep) block_sync<NT>();       // fwd allocation visible
                 PASS_MARK(0);
                 if (estep) {
                     fwd_off = sm.ll[1];
@@ -377,7 +380,9 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 int *fwd = (int *) (arena + fwd_off);
 
                 // (a typed locus is one group: the ordinal is the state, or state * 2 + orientation at a heterozygous one)
-                const bool one_group = ng == 1, het0 = sm.gx[0] != sm.gy[0];
+                const bool one_group = ng == 1;
+                const int gx0 = typed ? g0 : sm.gx[0], gy0 = typed ? g1 : sm.gy[0];
+                const bool het0 = gx0 != gy0;
                 auto decode = [&](int c, int &g, int &s, int &dir) {
                     g = 0;
                     if (one_group) { s = het0 ? c >> 1 : c; dir = het0 ? (c & 1) : 0; return; }
@@ -402,9 +407,10 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         const int4 *ra = succ16 + (size_t) pa * A, *rb = succ16 + (size_t) pb * A;
 #pragma unroll 1
                         for (int g = 0; g < ng; ++g) {
-                            const int x = sm.gx[g], y = sm.gy[g];
+                            int x = gx0, y = gy0, gb = 0;
+                            if (!one_group) { x = sm.gx[g]; y = sm.gy[g]; gb = sm.gbase[g]; }
                             const bool het = x != y;
-                            const int c0 = sm.gbase[g] + (het ? 2 * s : s);
+                            const int c0 = gb + (het ? 2 * s : s);
                             const int nd = het ? 2 : 1;
                             int4 ea[2], eb[2];
                             ea[0] = ea[1] = eb[0] = eb[1] = make_int4(-1, 0, 0, 0);
@@ -464,11 +470,13 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                 // new states / arrivals of the step
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { my_new += __shfl_xor_sync(FULL, my_new, o); my_arr += __shfl_xor_sync(FULL, my_arr, o); }
-                if (lane == 0 && my_arr) { atomicAdd(&sm.ints[4], my_new); atomicAdd(&sm.ints[5], my_arr); }
+                if (lane == 0 && my_arr) { atomicAdd(&cn[0], my_new); atomicAdd(&cn[1], my_arr); }
                 block_sync<NT>();
                 PASS_MARK(1);
-                S_out = sm.ints[4];
-                const int n_arr = sm.ints[5];
+                S_out = cn[0];
+                const int n_arr = cn[1];
+                if (tid < 4) sm.cnts[par ^ 1][tid] = 0;         // the next step's set: its last users finished before the previous end-of-step barrier
+                else if (tid < 12) sm.look[par ^ 1][tid - 4] = 0;
                 if (S_out == 0) { rc = 1; break; }      // every extension died: m_haplopairs[i+1] empty, HaploBuilder.cpp:80-82 (nothing was inserted)
                 if (S_out > sc.scap || S_out >= MAX_STATES_PER_LOCUS) { status = ST_TOO_BIG; reset_table(); rc = 2; break; }
                 if (tid == 0) sm.ll[1] = alloc(block_layout(S_out, n_arr, p.estep).total);
@@ -524,12 +532,12 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         unsigned long long prevp = 0;
                         if (lane == 0) {
                             if (tile > 0) {
-                                volatile unsigned long long *slot = &sm.look[(tile - 1) & 7];
+                                volatile unsigned long long *slot = &lk[(tile - 1) & 7];
                                 const unsigned long long want = (unsigned long long) (tile & 0xFFFF);
                                 do { prevp = *slot; } while ((prevp >> 48) != want);
                             }
                             const unsigned long long b_idx = (prevp >> 24) & 0xFFFFFFull, b_off = prevp & 0xFFFFFFull;
-                            *(volatile unsigned long long *) &sm.look[tile & 7] =
+                            *(volatile unsigned long long *) &lk[tile & 7] =
                                 ((unsigned long long) ((tile + 1) & 0xFFFF) << 48) | ((b_idx + (unsigned long long) __popc(crm)) << 24) | (b_off + (unsigned long long) tot_ar);
                         }
                         prevp = __shfl_sync(FULL, prevp, 0);
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         const int idx = (int) ((prevp >> 24) & 0xFFFFFFull) + __popc(crm & lt_mask);
                         const int off = (int) (prevp & 0xFFFFFFull) + xa - nn;
                         const u32 rev = ((u32) enc >> 30) & 1u;
-                        const int gxv = sm.gx[g], gyv = sm.gy[g];
+                        const int gxv = one_group ? gx0 : sm.gx[g], gyv = one_group ? gy0 : sm.gy[g];
                         const int xx = dir ? gyv : gxv, yy = dir ? gxv : gyv;
                         const int hpa = (int) (key >> 32), hpb = (int) (key & 0xFFFFFFFFu);
                         ST_OUT(t_ida + idx, hpa); ST_OUT(t_idb + idx, hpb);
@@ -571,14 +579,14 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         }
                         else {
                             tab.created(h, (u32) idx, (u32) off);     // ord = state index (never equals an ordinal), cnt = 0 (the scatter counts again), soff
-                            if (nn <= 8) mlist[atomicAdd(&sm.ints[6], 1)] = make_int2(idx, (int) h);
-                            else mlist[mcap - 1 - atomicAdd(&sm.ints[7], 1)] = make_int2(idx, (int) h);
+                            if (nn <= 8) mlist[atomicAdd(&cn[2], 1)] = make_int2(idx, (int) h);
+                            else mlist[mcap - 1 - atomicAdd(&cn[3], 1)] = make_int2(idx, (int) h);
                         }
                     }
                 }
                 block_sync<NT>();
                 PASS_MARK(2);
-                const int n_light = sm.ints[6], n_heavy = sm.ints[7];
+                const int n_light = cn[2], n_heavy = cn[3];
 
                 // ---- pass D: scatter the arrivals of multi-arrival states (unordered inside a segment; ordered in E) ----
                 if (n_light + n_heavy > 0) {
@@ -634,7 +642,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                         alpha = (q == 0) ? term : __dadd_rn(alpha, term);
                         if (!estep) {
                             vmax = fmax(vmax, in_v1[s]);
-                            ST_OUT(t_arr + a0 + q, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
+                            ST_OUT(t_arr + a0 + q, (u32) s | ((one_group ? het0 : sm.gx[g] != sm.gy[g]) ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
                         }
                     }
                     ST_OUT(t_alpha + idx, alpha);
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG 
                             term = __dmul_rn(in_alpha[s], tv);
                             if (!estep) {
                                 vmax = fmax(vmax, in_v1[s]);
-                                ST_OUT(t_arr + a0 + b0 + lane, (u32) s | (sm.gx[g] != sm.gy[g] ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
+                                ST_OUT(t_arr + a0 + b0 + lane, (u32) s | ((one_group ? het0 : sm.gx[g] != sm.gy[g]) ? ARR_HET : 0u) | (((u32) e >> 31) ? ARR_REV : 0u));
                             }
                         }
                         const int lim = min(32, n - b0);
