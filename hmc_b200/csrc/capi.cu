@@ -555,6 +555,11 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
     ctx->kb_work[0] = hc[24]; ctx->kb_work[1] = hc[25]; ctx->kb_work[2] = hc[26];
     if (getenv("HMC_B200_PRINT_KBEST")) fprintf(stderr, "kbest: %lld lazy-next visits, %lld nodes, %lld eager-list states\n", hc[24], hc[25], hc[26]);
+#ifdef HMC_PROFILE_PASSES
+    if (getenv("HMC_B200_PRINT_KBEST") && count > 0)
+        fprintf(stderr, "kbest Mcycles per individual: P(G) + eager %.2f, enumeration %.2f, traceback %.2f; longest individual %.2f\n", hc[27] / 1e6 / count, hc[28] / 1e6 / count,
+                hc[29] / 1e6 / count, hc[30] / 1e6);
+#endif
     ctx->last_K = K; ctx->last_estep = estep;
     if (estep && waves == 1) {
         ctx->ecache.first = first; ctx->ecache.count = count; ctx->ecache.flags = flags; ctx->ecache.fp = fp; ctx->ecache.n_wave = fp.n_wave;

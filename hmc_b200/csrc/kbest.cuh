@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
             w = __shfl_sync(FULL, w, 0);
         }
         if (__ldcg(p.status + w) != ST_DONE) continue;
+#ifdef HMC_PROFILE_PASSES
+        const long long kt0 = clock64();
+#endif
         const int row = p.wave[w] - p.first;
         const LocusRec *rec = p.loci + (size_t) w * loci_stride(L);
         const int *lexp = p.locus_exp ? p.locus_exp + (size_t) w * exp_stride(L) : nullptr;
@@ -302,6 +305,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
         }
         if (nomem) { if (lane == 0) p.status[w] = ST_NOMEM_KBEST; continue; }
 
+#ifdef HMC_PROFILE_PASSES
+        const long long kt1 = clock64();
+#endif
         // ---- the K best links over the final states ----
         double my_prior = 0.0;      // lane r: prior of result r
         int n_sel = 0;
@@ -502,6 +508,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
         }
         if (nomem) { if (lane == 0) p.status[w] = ST_NOMEM_KBEST; continue; }
 
+#ifdef HMC_PROFILE_PASSES
+        const long long kt2 = clock64();
+#endif
         // ---- priors, posteriors, coverage (HaploBuilder.cpp:105-116) ----
         double cov = 0.0;
         for (int r = 0; r < n_sel; ++r) {
@@ -586,6 +595,13 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
             }
         }
         __syncwarp();
+#ifdef HMC_PROFILE_PASSES
+        if (lane == 0) {    // cycles: P(G) + eager lists, enumeration, traceback; the longest individual
+            const long long kt3 = clock64();
+            atomicAdd(p.work + 3, (unsigned long long) (kt1 - kt0)); atomicAdd(p.work + 4, (unsigned long long) (kt2 - kt1)); atomicAdd(p.work + 5, (unsigned long long) (kt3 - kt2));
+            atomicMax(p.work + 6, (unsigned long long) (kt3 - kt0));
+        }
+#endif
     }
     if (lane == 0) { atomicAdd(p.work + 0, n_next); atomicAdd(p.work + 1, n_nodes); atomicAdd(p.work + 2, n_eager); }
 }

@@ -53,6 +53,20 @@ def test_klists_are_sorted_normalised_and_prefix_stable(c2):
     assert np.array_equal(r4["prior"], r["prior"][:, :4])
 
 
+def test_streamed_kbest_equals_the_serial_order(c2, monkeypatch):
+    """K2 runs beside the forward kernel and takes individuals as they finish (done list, own arena region); running it after the
+    forward kernel instead (HMC_B200_KBEST_SERIAL=1) must give the same bits -- full C2, every array."""
+    r, dev = c2["r10"], c2["dev"]
+    monkeypatch.setenv("HMC_B200_KBEST_SERIAL", "1")
+    s = dev.resolve_all(K=10)
+    monkeypatch.delenv("HMC_B200_KBEST_SERIAL")
+    for k in ("pg", "exp", "coverage", "nres", "prior", "posterior", "haps"):
+        assert np.array_equal(s[k], r[k]), k
+    again = dev.resolve_all(K=10)                       # and the streamed pass is reproducible run to run
+    for k in ("pg", "prior", "haps"):
+        assert np.array_equal(again[k], r[k]), k
+
+
 def test_shard_invariance(c2):
     r, dev = c2["r10"], c2["dev"]
     a = dev.resolve_all(K=10, first=0, count=700)
