@@ -1,0 +1,16 @@
+#!/bin/bash
+# last evidence pass of the round: new test, K-best phase timers, bench line, ncu captures of the final sources
+cd $GRAFT_REPO_ROOT
+make -C oracle -s
+timeout 600 python -m pytest tests/test_gpu_properties.py tests/test_gpu_emit.py -x -q 2>&1 | tail -2
+HMC_B200_LIB=$PWD/build/var/libhmc_prof.so HMC_B200_PRINT_KBEST=1 timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | grep kbest > gpurun_out/kbest_phases.txt
+cat gpurun_out/kbest_phases.txt
+python bench.py --steps 5 --warmup 3 > gpurun_out/r2_final_bench_N1.json 2> gpurun_out/r2_final_bench.err || exit 1
+CMD="python bench.py --steps 2 --warmup 1"
+export HMC_BENCH_EPASS_REPS=1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_final_bench_launches.csv $CMD > gpurun_out/ncu_f1.log 2>&1
+export HMC_BENCH_SKIP_EPASS=1
+ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s 2 -c 1 -o gpurun_out/r2_final_forward_full $CMD > gpurun_out/ncu_f2.log 2>&1
+tail -1 gpurun_out/ncu_f2.log
+ncu --set full --clock-control none --import-source on -k regex:kbest_kernel -s 2 -c 1 -o gpurun_out/r2_final_kbest_full $CMD > gpurun_out/ncu_f3.log 2>&1
+tail -1 gpurun_out/ncu_f3.log
