@@ -395,15 +395,27 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
             u32 cur = top;
             bool up = false;            // the previous visit was of the pending stream's predecessor, which ...
             double up_v = -1.0;         // ... appended this link (< 0: it ran dry instead)
+            // a visit that descends has already read its predecessor whole (header + streams, in the trip that fetched the wanted link): carried over
+            bool have = false;
+            uint4 c_hdr = make_uint4(0, 0, 0, 0);
+            double2 c_tf = make_double2(0.0, 0.0);
+            double c_head = -1.0;
+            u32 c_sw = 0, c_sn = 0;
+            int c_j = 0;
             for (;;) {
                 __syncwarp();
                 KbNode nd = node_at(cur);
-                const uint4 hdr = *reinterpret_cast<const uint4 *>(nd.b);           // level, state, next, {nD, nS, pending, exhausted}
-                const double2 tf = *reinterpret_cast<const double2 *>(nd.b + 16);   // tpv, fac
+                uint4 hdr;
+                double2 tf;
                 double my_head = -1.0;
                 u32 my_sw = 0, my_sn = 0;
                 int my_j = 0;
-                if (lane < K) { my_head = nd.head()[lane]; my_sw = nd.sword()[lane]; my_sn = nd.snode()[lane]; my_j = nd.sj()[lane]; }
+                if (have) { hdr = c_hdr; tf = c_tf; my_head = c_head; my_sw = c_sw; my_sn = c_sn; my_j = c_j; have = false; }
+                else {
+                    hdr = *reinterpret_cast<const uint4 *>(nd.b);           // level, state, next, {nD, nS, pending, exhausted}
+                    tf = *reinterpret_cast<const double2 *>(nd.b + 16);     // tpv, fac
+                    if (lane < K) { my_head = nd.head()[lane]; my_sw = nd.sword()[lane]; my_sn = nd.snode()[lane]; my_j = nd.sj()[lane]; }
+                }
                 const int ns = (int) ((hdr.w >> 8) & 0xFFu), pend = (int) ((hdr.w >> 16) & 0xFFu);
                 const int k = (int) (hdr.w & 0xFFu);
                 if (lane >= ns) { my_head = -1.0; my_sw = 0; my_sn = 0; my_j = 0; }
@@ -419,15 +431,22 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
                                 pref = find_or_create((int) hdr.x - 1, (int) (__shfl_sync(FULL, my_sw, pend) & ARR_PRED_MASK));
                                 if (!pref) return;
                                 if (lane == pend) { my_sn = pref; nd.snode()[pend] = pref; }
+                                // the link this stream supplied (its first: index k - 1 here) did not know its predecessor's node yet: the traceback follows nodes
+                                if (lane == 0 && k > 0) nd.dnode()[k - 1] = pref;
                             }
                             KbNode pd = node_at(pref);
-                            const u32 pw = *reinterpret_cast<const u32 *>(pd.b + 12);
+                            c_hdr = *reinterpret_cast<const uint4 *>(pd.b);
+                            c_tf = *reinterpret_cast<const double2 *>(pd.b + 16);
                             const double pj = pd.dv()[j];           // (read before it is known to be valid: inside the node)
+                            c_head = -1.0; c_sw = 0; c_sn = 0; c_j = 0;
+                            if (lane < K) { c_head = pd.head()[lane]; c_sw = pd.sword()[lane]; c_sn = pd.snode()[lane]; c_j = pd.sj()[lane]; }
+                            const u32 pw = c_hdr.w;
                             if ((int) (pw & 0xFFu) > j) pv = pj;
                             else if (!(pw >> 24)) {     // the predecessor's list has to grow first
                                 if (lane == 0) stack[sp] = cur;
                                 ++sp;
                                 cur = pref;
+                                have = true;
                                 continue;
                             }
                         }
