@@ -331,21 +331,33 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
         // streams of a new node: the (up to K) arrivals with the best heads v1(pred) * tpv (* fac)
         auto init_streams = [&](KbNode nd, int n, double tpv, double fac, const double *pv1, auto word_of) {
             int ns = 0;
-            select_top(n, K,
-                       [&](int e) -> double {
-                           double v = __dmul_rn(pv1[word_of(e) & ARR_PRED_MASK], tpv);
-                           if (fac != 1.0) v *= fac;
-                           return v;
-                       },
-                       [&](int r, int e, double v) {
-                           if (lane == 0) { nd.head()[r] = v; nd.sword()[r] = word_of(e); nd.snode()[r] = 0; nd.sj()[r] = 0; }
-                           ns = r + 1;
-                       });
+            double h0 = -1.0;       // best head and its arrival word (stream 0), kept for the first link below
+            u32 sw0 = 0;
+            auto value_of = [&](int e) -> double {
+                double v = __dmul_rn(pv1[word_of(e) & ARR_PRED_MASK], tpv);
+                if (fac != 1.0) v *= fac;
+                return v;
+            };
+            if (n == 1) {           // a single arrival (two thirds of the states): one stream, nothing to select
+                const double v = value_of(0);
+                if (v >= 0.0) {
+                    sw0 = word_of(0); h0 = v; ns = 1;
+                    if (lane == 0) { nd.head()[0] = v; nd.sword()[0] = sw0; nd.snode()[0] = 0; nd.sj()[0] = 0; }
+                }
+            }
+            else
+                select_top(n, K, value_of,
+                           [&](int r, int e, double v) {
+                               const u32 wd = word_of(e);
+                               if (lane == 0) { nd.head()[r] = v; nd.sword()[r] = wd; nd.snode()[r] = 0; nd.sj()[r] = 0; }
+                               if (r == 0) { h0 = v; sw0 = wd; }
+                               ns = r + 1;
+                           });
             if (lane == 0) {
                 nd.tpv() = tpv; nd.fac() = fac; nd.nS() = (unsigned char) ns;
                 if (ns > 0) {       // the first link is the best head: stream 0 (select_top emits best first)
-                    const u32 sw = nd.sword()[0];
-                    nd.dv()[0] = nd.head()[0];
+                    const u32 sw = sw0;
+                    nd.dv()[0] = h0;
                     nd.dbp()[0] = (sw & ARR_PRED_MASK) | ((sw & ARR_REV) ? BP_REV : 0u);
                     nd.dnode()[0] = 0;
                     nd.sj()[0] = 1;
@@ -457,14 +469,17 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
                     }
                     if (lane == pend) { my_head = hv; nd.head()[pend] = hv; }
                 }
-                // take the best stream head (ties: the earlier stream)
+                // take the best stream head (ties: the earlier stream); a single stream needs no contest
                 double bv = my_head;
                 int be = lane;
+                if (ns == 1) { bv = __shfl_sync(FULL, my_head, 0); be = 0; }
+                else {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(FULL, bv, o);
-                    const int oe = __shfl_xor_sync(FULL, be, o);
-                    if (ov > bv || (ov == bv && oe < be)) { bv = ov; be = oe; }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ov = __shfl_xor_sync(FULL, bv, o);
+                        const int oe = __shfl_xor_sync(FULL, be, o);
+                        if (ov > bv || (ov == bv && oe < be)) { bv = ov; be = oe; }
+                    }
                 }
                 if (bv < 0.0) { if (lane == 0) *reinterpret_cast<u32 *>(nd.b + 12) = (hdr.w & 0x0000FFFFu) | (KB_NONE << 16) | (1u << 24); }
                 else {
