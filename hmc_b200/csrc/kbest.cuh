@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS == 1 ? KB1_MAXNR
             if (lane == 0) {
                 const volatile int *slot = p.done_list + w;
                 while ((w = *slot) < 0) __nanosleep(1000);
-                __threadfence();
             }
             w = __shfl_sync(FULL, w, 0);
+            __threadfence();        // every lane reads the trellis: each one orders its loads behind the list entry
         }
         if (__ldcg(p.status + w) != ST_DONE) continue;
 #ifdef HMC_PROFILE_PASSES

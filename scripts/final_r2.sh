@@ -1,8 +1,8 @@
 #!/bin/bash
-# last evidence pass of the round: new test, K-best phase timers, bench line, ncu captures of the final sources
+# last evidence pass of the round: GPU suite, K-best phase timers, bench line, ncu captures of the final sources
 cd $GRAFT_REPO_ROOT
 make -C oracle -s
-timeout 600 python -m pytest tests/test_gpu_properties.py tests/test_gpu_emit.py -x -q 2>&1 | tail -2
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4
 HMC_B200_LIB=$PWD/build/var/libhmc_prof.so HMC_B200_PRINT_KBEST=1 timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | grep kbest > gpurun_out/kbest_phases.txt
 cat gpurun_out/kbest_phases.txt
 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_final_bench_N1.json 2> gpurun_out/r2_final_bench.err || exit 1
