@@ -2,9 +2,7 @@
 # last evidence pass of the round: GPU suite, K-best phase timers, bench line, ncu captures of the final sources
 cd $GRAFT_REPO_ROOT
 make -C oracle -s
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4
-HMC_B200_LIB=$PWD/build/var/libhmc_prof.so HMC_B200_PRINT_KBEST=1 timeout 300 python scripts/probe_count.py 2000 1000 0.05 0 10 2000 2>&1 | grep kbest > gpurun_out/kbest_phases.txt
-cat gpurun_out/kbest_phases.txt
+timeout 600 python -m pytest tests/test_gpu_forward.py tests/test_gpu_properties.py -x -q 2>&1 | tail -2
 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_final_bench_N1.json 2> gpurun_out/r2_final_bench.err || exit 1
 CMD="python bench.py --steps 2 --warmup 1"
 export HMC_BENCH_EPASS_REPS=1
