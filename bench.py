@@ -187,19 +187,22 @@ def run_ours(args):
     dev.set_panel(host["geno"], host["n_alleles"], host["allele_freq"])
     dev.set_model(hmodel)
     flags = FLAG_PANEL_ROWS if world > 1 else 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    xch_ms = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    xch_ms, wait_ms = [], []
+    tiny = torch.zeros(1, device=cuda) if world > 1 else None
 
     def exchange():
         """The one exchange of a sharded resolveAll pass: in-place all-gather of the seven result arrays over the individuals (NCCL)."""
         if world == 1:
             return
+        ev[2].record()
+        dist.all_reduce(tiny)       # a rank that finished its block early waits HERE for the slowest one: reported apart from the transfer
         ev[0].record()
         for ptr, rb in dev.result_device_ptrs():
             allgather_rows_(device_view(ptr, n_ind * rb, torch.uint8, local), n_ind, rb, rank, world)
         ev[1].record()
         torch.cuda.synchronize()
-        xch_ms.append(ev[0].elapsed_time(ev[1]))
+        xch_ms.append(ev[0].elapsed_time(ev[1])); wait_ms.append(ev[2].elapsed_time(ev[0]))
 
     def step_device():
         dev.resolve_all_device(K=K_SAMPLE, first=first, count=count, flags=flags)
@@ -213,7 +216,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     fwd_ms, tb_ms, launches = [], [], 0
-    xch_ms.clear()
+    xch_ms.clear(); wait_ms.clear()
     t_begin = time.perf_counter()
     for _ in range(args.steps):
         step_device()
@@ -226,6 +229,11 @@ def run_ours(args):
     steps_per_pass = counters["steps"]
     dev_ms = float(np.mean(fwd_ms) + np.mean(tb_ms))        # CUDA-event time of the kernels of one pass (timed on their stream)
     exchange_ms = float(np.mean(xch_ms)) if xch_ms else 0.0
+    rank_wait_ms = float(np.mean(wait_ms)) if wait_ms else 0.0
+    per_rank_dev_ms = [dev_ms]
+    if world > 1:       # the ranks' own kernel times: the slowest block sets the pass
+        t = torch.zeros(world, dtype=torch.float64, device=cuda); t[rank] = dev_ms
+        dist.all_reduce(t); per_rank_dev_ms = [float(x) for x in t.tolist()]
 
     # ---- end to end through the C-ABI with host buffers (inputs and results in page-locked memory owned by the caller) ----
     res = None
@@ -375,7 +383,8 @@ def run_ours(args):
                                         if n_gpus > 1 else None},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "kernel_ms": {"forward": float(np.mean(fwd_ms)), "traceback": float(np.mean(tb_ms)), "device_total": dev_ms, "exchange": exchange_ms},
+        "kernel_ms": {"forward": float(np.mean(fwd_ms)), "traceback": float(np.mean(tb_ms)), "device_total": dev_ms, "exchange": exchange_ms, "rank_wait": rank_wait_ms,
+                      "per_rank_device_total": per_rank_dev_ms},
         "states_per_s": total_states / (elapsed / args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "HaploBuilder pass = forward (K1, the dominant launch) + lazy K-best / traceback (K2), rank 0; the algorithmic bytes of SURVEY 8d "

@@ -89,6 +89,7 @@ struct hmc_ctx {
     std::vector<int> h_order, h_rank;
     DevBuf<long long> d_work;       // forward-kernel cycles per individual of the last pass that resolved it (0 = not yet): the next pass's work order
     std::vector<long long> h_work;
+    long long seen_max_states = 0;  // most live states at one index over the passes on this panel: sizes the per-CTA spill scratch
     double est_units[2] = {0, 0};   // arena units (8 B) one individual's trellis took in the last waves, resolve / E-step mode: sizes the next wave
     std::vector<int> h_nall;
 
@@ -413,7 +414,14 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         ScratchPool &pl = big_mode ? ctx->big_pool : ctx->pool;
         int slots;
         if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, 1 << 20, 1 << 22, 1 << 23); }
-        else { slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, 1 << 16, 1 << 18, 1 << 19); }
+        // (131,072 states / 524,288 candidates per step and CTA, 35 MB of scratch each: an individual beyond that goes to the big-scratch wave, which
+        // runs AFTER this one -- at 65,536 a single 71,425-state individual of an 8,000-individual cohort cost its rank a second wave of 39 ms)
+        // Once a pass over this panel has seen a bigger individual the scratch grows to 262,144 states (69 MB per CTA) for the passes that follow:
+        // EM iterations resolve the same individuals again.
+        else {
+            const int sh = ctx->seen_max_states > 124000 ? 18 : 17;
+            slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, 1 << sh, 1 << (sh + 2), 1 << (sh + 3));
+        }
         if (rc) return rc;
         ctx->h_wave.assign(pending.begin(), pending.begin() + n_wave);
         CK(cudaMemcpyAsync(ctx->d_wave.p, ctx->h_wave.data(), sizeof(int) * n_wave, cudaMemcpyHostToDevice, ctx->stream));
@@ -550,6 +558,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
                                     100.0 * hc[32 + b] / tc, (double) hc[32 + b] / hc[50 + b]);
     }
 #endif
+    ctx->seen_max_states = std::max<long long>(ctx->seen_max_states, hc[2]);
     ctx->counters[HMC_CNT_STEPS] = hc[0]; ctx->counters[HMC_CNT_STATES] = hc[1]; ctx->counters[HMC_CNT_MAX_STATES] = hc[2];
     ctx->counters[HMC_CNT_ARRIVALS] = hc[3]; ctx->counters[HMC_CNT_SPILL_STEPS] = hc[5]; ctx->counters[HMC_CNT_ESTEP_ENTRIES] = hc[7];
     ctx->counters[HMC_CNT_WAVES] = waves; ctx->counters[HMC_CNT_LAUNCHES] = launches;
@@ -633,7 +642,7 @@ int hmc_set_panel(hmc_ctx *ctx, int N, int L, int Amax, const int8_t *geno, cons
     ctx->have_model = false;        // the automaton tables (successor stride, head table) belong to the previous panel's allele tables
     ctx->r_count = 0;
     ctx->h_work.clear();
-    ctx->est_units[0] = ctx->est_units[1] = 0;
+    ctx->est_units[0] = ctx->est_units[1] = 0; ctx->seen_max_states = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax;
     ctx->bits = Amax + 1 <= 4 ? 2 : (Amax + 1 <= 16 ? 4 : 8);
     const int per = 32 / (2 * ctx->bits);
@@ -689,7 +698,7 @@ int hmc_set_panel_packed(hmc_ctx *ctx, int N, int L, int Amax, int bits, const u
     ctx->have_model = false;
     ctx->r_count = 0;
     ctx->h_work.clear();
-    ctx->est_units[0] = ctx->est_units[1] = 0;
+    ctx->est_units[0] = ctx->est_units[1] = 0; ctx->seen_max_states = 0;
     ctx->N = N; ctx->L = L; ctx->Amax = Amax; ctx->bits = bits;
     const int per = 32 / (2 * bits);
     ctx->words = (L + per - 1) / per;
