@@ -291,6 +291,7 @@ static cudaError_t launch_forward(int nt, const FwdParams &p, int grid, cudaStre
         case 32: return launch_forward_t<32, 128, 16>(p, grid, st, occ);
         case 64: return launch_forward_t<64, 128, 12>(p, grid, st, occ);
         case 128: return launch_forward_t<128, 256, 4>(p, grid, st, occ);
+        case 1024: return launch_forward_t<1024, 256, 1>(p, grid, st, occ);     // the big-scratch wave: few CTAs, an SM each -- 32 warps instead of 8 on its giant steps
         default: return launch_forward_t<256, 256, 3>(p, grid, st, occ);
     }
 }
@@ -416,10 +417,12 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         if (big_mode) { slots = std::min(n_wave, 16); rc = build_pool(ctx, pl, slots, 1 << 20, 1 << 22, 1 << 23); }
         // (131,072 states / 524,288 candidates per step and CTA, 35 MB of scratch each: an individual beyond that goes to the big-scratch wave, which
         // runs AFTER this one -- at 65,536 a single 71,425-state individual of an 8,000-individual cohort cost its rank a second wave of 39 ms)
-        // Once a pass over this panel has seen a bigger individual the scratch grows to 262,144 states (69 MB per CTA) for the passes that follow:
-        // EM iterations resolve the same individuals again.
+        // Not more: an individual of several 100,000 states takes seconds on ONE 256-thread CTA that shares its SM, and the whole wave waits for it
+        // (C4: 10,000 x 2,000 with individuals of up to 553,127 states ran 5.8 s with 262,144-state scratch, 3.1 s when they go to the big-scratch wave,
+        // where 16 CTAs have an SM each).  HMC_B200_SCRATCH_SHIFT overrides (16..18).
         else {
-            const int sh = ctx->seen_max_states > 124000 ? 18 : 17;
+            int sh = 17;
+            if (const char *e = getenv("HMC_B200_SCRATCH_SHIFT")) sh = std::min(18, std::max(16, atoi(e)));
             slots = std::min(n_wave, max_slots); rc = build_pool(ctx, pl, slots, 1 << sh, 1 << (sh + 2), 1 << (sh + 3));
         }
         if (rc) return rc;
@@ -455,7 +458,7 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        CK(launch_forward(nt, fp, slots, ctx->stream, nullptr));
+        CK(launch_forward(big_mode && !getenv("HMC_B200_BIG_NARROW") ? 1024 : nt, fp, slots, ctx->stream, nullptr));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ++launches;
         if (!estep) {
@@ -494,8 +497,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
         h_status.resize(n_wave);
         CK(cudaMemcpyAsync(h_status.data(), ctx->d_status.p, sizeof(int) * n_wave, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->kernel_ms[0] += ms;
+        float ms = 0, wave_fwd_ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->kernel_ms[0] += ms; wave_fwd_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->kernel_ms[1] += ms;
         rc = after_wave(fp, n_wave, h_status, launches);
         if (rc) return rc;
@@ -532,7 +535,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             for (int q = 0; q < n_wave; ++q) ++hist[h_status[q] & 7];
             unsigned long long cur = 0;
             cudaMemcpy(&cur, ctx->d_cursor.p, sizeof cur, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "wave %d: %d individuals -> pending %d done %d nomem %d too_big %d no_head %d nomem_kbest %d; arena cursor %.1f of %.1f GB (forward share %.2f)\n", waves, n_wave,
+            fprintf(stderr, "wave %d (forward %.1f ms, %d CTAs%s): %d individuals -> pending %d done %d nomem %d too_big %d no_head %d nomem_kbest %d; arena cursor %.1f of %.1f GB (forward share %.2f)\n", waves,
+                    wave_fwd_ms, slots, big_mode ? ", big scratch" : "", n_wave,
                     hist[ST_PENDING], hist[ST_DONE], hist[ST_NOMEM], hist[ST_TOO_BIG], hist[ST_NO_HEAD], hist[ST_NOMEM_KBEST], cur * 8 / 1e9, ctx->d_arena.n * 8 / 1e9, fwd_share);
         }
         // every individual of the wave ran out of arena: the first one had it to itself (the queue hands them out in order), so it can never fit

@@ -123,7 +123,7 @@ struct FwdSmem {
 };
 
 template <int NT, int CC, int MINB, bool ESTEP>
-__global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG : 255) forward_kernel(FwdParams p)
+__global__ void __launch_bounds__(NT, MINB) __maxnreg__(NT == 256 ? FWD_MAXNREG : (NT > 512 ? 64 : 255)) forward_kernel(FwdParams p)
 {
     typedef FwdSmem<NT, CC> Smem;
     extern __shared__ __align__(16) unsigned char smem_raw[];

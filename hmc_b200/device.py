@@ -71,8 +71,9 @@ def lib():
         L.hmc_fetch_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hmc_stream.restype = C.c_void_p
         L.hmc_stream.argtypes = [C.c_void_p]
-        L.hmc_get_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.hmc_format_best.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
+        if hasattr(L, "hmc_get_likelihood"):       # (absent from older builds loaded through HMC_B200_LIB for A/B timing)
+            L.hmc_get_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.hmc_format_best.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
