@@ -458,7 +458,8 @@ static int run_waves(hmc_ctx *ctx, int first, int count, int K, unsigned flags, 
             CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        CK(launch_forward(big_mode && !getenv("HMC_B200_BIG_NARROW") ? 1024 : nt, fp, slots, ctx->stream, nullptr));
+        // (the wide configuration of the big-scratch wave is measured and parity-tested in resolve mode only: C4)
+        CK(launch_forward(big_mode && !estep && !getenv("HMC_B200_BIG_NARROW") ? 1024 : nt, fp, slots, ctx->stream, nullptr));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ++launches;
         if (!estep) {
