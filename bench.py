@@ -11,6 +11,9 @@ genotypes, default HMC options); the metric counts individual x locus extensions
 `value`   = device-resident throughput (panel + model already in HBM, results left in HBM)
 `e2e`     = the same pass through the C-ABI with HOST buffers: panel + model H2D, results D2H every step
 `roofline`= algorithmic bytes of the HaploBuilder pass / CUDA-event time of its kernels (K1 + K2) vs the measured HBM copy peak
+`kernel_ms`= CUDA-event times of one pass on this rank's kernel stream: forward (K1, with the streamed K2 warps beside it), traceback (what is left
+            of K2 after K1), their sum; with N > 1 also the in-place NCCL all-gather (`exchange`), the wait for the slowest rank before it
+            (`rank_wait`) and every rank's kernel time (`per_rank_device_total`)
 `cpu_baseline` = the oracle port timed on a bounded sample of the same workload on this host (1 core); its results are compared with
                  the device's for the same individuals (`parity_checked`)
 """
