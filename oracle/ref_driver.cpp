@@ -30,7 +30,7 @@ static double now_s()
 
 struct DriverOpts {
 	string input, dump, out_suffix;
-	bool dump_states = false, dump_beta = false, dump_estep = false, dump_patterns = true, dump_klist = true;
+	bool dump_states = false, dump_beta = false, dump_estep = false, dump_patterns = true, dump_klist = true, dump_likelihood = false;
 	int time_resolve = 0, time_estep = 0, time_offset = 0, time_steps = 1, time_warmup = 0;
 	DriverOpts() : out_suffix(".reconstructed") {}
 };
@@ -180,6 +180,10 @@ public:
 			fprintf(stderr, "[hmc_ref] iter %d  resolveAll %.3f s  LL = %f  switch = %f\n", iter, t_res, ll, compare.switch_error());
 			if (opt.dump_klist || opt.dump_states) dumpIndividuals(sample_size);
 			if (opt.dump_estep) dumpEstep();
+			if (opt.dump_likelihood && fp) {	// HaploBuilder::getLikelihood (HaploBuilder.cpp:128-151) of both haplotypes of every resolution, under this iteration's model
+				for (int i = 0; i < resolved.genotype_num(); ++i)
+					fprintf(fp, "lk %d %a %a %a\n", i, getLikelihood(resolved[i](0)), getLikelihood(resolved[i](1)), getLikelihood(resolved[i]));
+			}
 
 			if (iter < max_iteration && ll >= old_ll && (old_ll - ll) / old_ll > 0.0001) {
 				t0 = now_s();
@@ -253,7 +257,7 @@ static void usage()
 		"  model options (names and defaults of HMC.cpp:19-56): -m/--model MV|MC|MA, -r/--min-freq-rel x,\n"
 		"    -a/--min-freq-abs 1.5, -n/--num-patterns n, --min-pattern-len 1, --max-pattern-len 30, -o/--mc-order 1,\n"
 		"    --exact-estimate, --sample-size 10, -i/--max-iteration 1, -d/--debug 2\n"
-		"  driver options: --dump FILE [--dump-states] [--dump-beta] [--dump-estep] [--no-patterns] [--no-klist]\n"
+		"  driver options: --dump FILE [--dump-states] [--dump-beta] [--dump-estep] [--dump-likelihood] [--no-patterns] [--no-klist]\n"
 		"    --out-suffix S (default .reconstructed; 'none' to skip), --time-resolve n [--time-estep m]\n"
 		"    --compare REAL.phase: HaploComp of the positional (inferred) file against REAL, printed as hex floats\n");
 }
@@ -291,6 +295,7 @@ int main(int argc, char **argv)
 		else if (a == "--dump-states") m.opt.dump_states = true;
 		else if (a == "--dump-beta") m.opt.dump_beta = true;
 		else if (a == "--dump-estep") m.opt.dump_estep = true;
+		else if (a == "--dump-likelihood") m.opt.dump_likelihood = true;
 		else if (a == "--no-patterns") m.opt.dump_patterns = false;
 		else if (a == "--no-klist") m.opt.dump_klist = false;
 		else if (a == "--out-suffix") m.opt.out_suffix = next();

@@ -84,6 +84,8 @@ def load(path: str) -> dict:
                 ind["cnt"] = tuple(int(x) for x in t[2:5])
             elif k == "counters":
                 it["counters"] = dict(steps=int(t[1]), states=int(t[2]), max_states=int(t[3]), arrivals=int(t[4]))
+            elif k == "lk":
+                it.setdefault("lk", []).append((fh(t[2]), fh(t[3]), fh(t[4])))
             elif k == "estep":
                 P = int(t[1])
                 it["estep"] = dict(freq=np.zeros(P), prefix=np.zeros(P), tp=np.zeros(P))

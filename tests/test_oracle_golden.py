@@ -104,3 +104,18 @@ def test_em_trace(name):
     rec = read_phase_idx(os.path.join(GOLDEN, name + ".phase.reconstructed"), d["sym"])
     for i in range(d["N"]):
         assert same_unordered_pair(o.resolution(i), rec[i]), i
+
+
+@pytest.mark.parametrize("name", ["g1_clean", "g2_missing", "g3_multi", "g8_head2", "g9_k1"])
+def test_get_likelihood_golden(name):
+    """getLikelihood(Haplotype) / (Genotype) of the reference on its own reconstructions (tests/golden/likelihood.json, written by
+    tests/golden/make_likelihood.py from the unmodified reference) == the oracle's restatement, bit for bit."""
+    import json
+    d = golden(name)
+    want = np.array([[float.fromhex(x) for x in row] for row in json.load(open(os.path.join(GOLDEN, "likelihood.json")))[name]])
+    rec = read_phase_idx(os.path.join(GOLDEN, name + ".phase.reconstructed"), d["sym"])        # what the reference resolved
+    o = Oracle(d["geno"], **model_opts(name))
+    o.find_patterns()
+    got = o.likelihood(rec.reshape(-1, d["L"])).reshape(-1, 2)
+    assert np.array_equal(got, want[:, :2])
+    assert np.array_equal(got[:, 0] * got[:, 1], want[:, 2])

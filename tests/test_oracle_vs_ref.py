@@ -73,3 +73,26 @@ def test_config0_c1_200x100_defaults(tmp_path):
         assert a["pg"] == b["pg"] and np.array_equal(a["prior"], np.array(b["prior"]))
         for k in range(a["n"]):
             assert np.array_equal(a["haps"][k], b["haps"][k])
+
+
+@pytest.mark.parametrize("kw,kind", [(dict(n_ind=40, n_loci=30, founders=5, missing=0.05, seed=111), "S"),
+                                     (dict(n_ind=30, n_loci=24, alleles=5, founders=6, missing=0.04, seed=112), "M")])
+def test_get_likelihood_of_the_reference(tmp_path, kw, kind):
+    """HaploBuilder::getLikelihood (HaploBuilder.cpp:128-151) is dead code in the reference's CLI; the driver calls it on both haplotypes of
+    every resolution and on the genotype.  The oracle's restatement (one trie descent per index) equals it bit for bit -- and the device's
+    automaton walk equals the oracle's (tests/test_gpu_emit.py), which pins hmc_get_likelihood to the reference."""
+    g = make_panel(**kw)
+    phase = str(tmp_path / "p.phase")
+    dump = str(tmp_path / "p.dump")
+    write_phase(phase, g, kind=kind)
+    subprocess.check_call([REF, phase, "--dump", dump, "--out-suffix", "none", "--dump-likelihood", "-d", "1"], stderr=subprocess.DEVNULL)
+    d = refdump.load(dump)
+    lk = np.array(d["iters"][0]["lk"])                       # [N][3]: haplotype 0, haplotype 1, genotype
+    assert lk.shape == (d["N"], 3) and (lk[:, :2] > 0).all()
+    o = Oracle(d["geno"])
+    o.find_patterns()
+    o.resolve_all()
+    haps = np.stack([o.resolution(i) for i in range(d["N"])])      # the reference's resolutions (bit-identical, checked above)
+    mine = o.likelihood(haps.reshape(-1, d["L"])).reshape(-1, 2)
+    assert np.array_equal(mine, lk[:, :2])
+    assert np.array_equal(mine[:, 0] * mine[:, 1], lk[:, 2])        # the Genotype overload is the product of the two
